@@ -1,0 +1,66 @@
+"""ctypes binding of include/poseidon252_b200.h.  The library MUST be present: there is no Python
+or CPU fallback for any batch entry point (loading fails loudly with instructions)."""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libposeidon252_b200.so")
+_LIB = None
+
+c_void_p, c_size_t, c_int, c_uint64 = ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int, ctypes.c_uint64
+
+# name -> (restype, argtypes): every symbol include/poseidon252_b200.h declares
+SIGNATURES = {
+    "p252_version": (ctypes.c_char_p, []),
+    "p252_strerror": (ctypes.c_char_p, [c_int]),
+    "p252_device_count": (c_int, [ctypes.POINTER(c_int)]),
+    "p252_create": (c_int, [c_int, ctypes.POINTER(c_void_p)]),
+    "p252_create_on_stream": (c_int, [c_int, c_void_p, ctypes.POINTER(c_void_p)]),
+    "p252_destroy": (None, [c_void_p]),
+    "p252_sync": (c_int, [c_void_p]),
+    "p252_last_error": (ctypes.c_char_p, [c_void_p]),
+    "p252_launch_count": (c_uint64, [c_void_p]),
+    "p252_host_alloc": (c_int, [c_size_t, ctypes.POINTER(c_void_p)]),
+    "p252_host_free": (c_int, [c_void_p]),
+    "p252_domain_separator": (c_int, [c_int, ctypes.POINTER(c_uint64)]),
+    "p252_tag_input": (c_int, [c_void_p, c_size_t, c_uint64, c_void_p, ctypes.POINTER(c_size_t)]),
+    "p252_hash_to_scalar": (c_int, [c_void_p, c_size_t, c_void_p]),
+    "p252_tag": (c_int, [c_void_p, c_size_t, c_uint64, c_void_p]),
+    "p252_hash_tag": (c_int, [c_int, c_size_t, c_size_t, c_void_p]),
+    "p252_encryption_tag": (c_int, [c_size_t, c_void_p]),
+    "p252_permute_batch": (c_int, [c_void_p, c_void_p, c_size_t, c_int]),
+    "p252_permute_batch_dense": (c_int, [c_void_p, c_void_p, c_size_t, c_int]),
+    "p252_digest_batch": (c_int, [c_void_p, c_void_p, c_void_p, c_size_t, c_size_t, c_void_p, c_size_t, c_int]),
+    "p252_hash_batch": (c_int, [c_void_p, c_int, c_void_p, c_size_t, c_size_t, c_void_p, c_size_t, c_int]),
+    "p252_encrypt_batch": (c_int, [c_void_p, c_void_p, c_size_t, c_size_t, c_void_p, c_void_p, c_void_p, c_int]),
+    "p252_decrypt_batch": (c_int, [c_void_p, c_void_p, c_size_t, c_size_t, c_void_p, c_void_p, c_void_p, c_void_p,
+                                   ctypes.POINTER(c_size_t), c_int]),
+    "p252_merkle4_level": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p, c_int]),
+    "p252_merkle4_tree_nodes": (c_int, [c_size_t, ctypes.POINTER(c_size_t), ctypes.POINTER(c_int)]),
+    "p252_merkle4_build": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p, c_int]),
+    "p252_dist_unique_id": (c_int, [c_void_p]),
+    "p252_dist_init": (c_int, [c_void_p, c_void_p, c_int, c_int]),
+    "p252_dist_finalize": (c_int, [c_void_p]),
+    "p252_merkle4_build_dist": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p, c_int]),
+}
+
+MEM_HOST, MEM_DEVICE, ASYNC = 0, 1, 2
+NCCL_UNIQUE_ID_BYTES = 128
+
+
+def lib():
+    """Load libposeidon252_b200.so (built in-tree by `python -m poseidon252_b200.build`)."""
+    global _LIB
+    if _LIB is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(
+                "poseidon252_b200: %s is missing. Build the sm_100a library first "
+                "(`python -m poseidon252_b200.build` or __graft_entry__.build()). "
+                "There is no CPU fallback for the batch path." % LIB_PATH)
+        handle = ctypes.CDLL(LIB_PATH, mode=ctypes.RTLD_GLOBAL)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(handle, name)       # AttributeError = header/library mismatch: fail loudly
+            fn.restype = res
+            fn.argtypes = args
+        _LIB = handle
+    return _LIB

@@ -1,0 +1,654 @@
+// C ABI of poseidon252_b200 (include/poseidon252_b200.h): context, host-side sponge bookkeeping
+// (io-pattern checks, tag derivation), staging for HOST buffers, kernel launches, and the
+// multi-GPU arity-4 tree build (one process per GPU, NCCL all-gather per level).
+//
+// Mirrors, for the batch path, the reference's public surface (/root/reference/src/lib.rs:13-31):
+//   Hash / Domain / io_pattern      src/hash.rs:21-155      -> p252_hash_tag, p252_hash_batch
+//   encrypt / decrypt               src/encryption.rs:62-95 -> p252_encrypt_batch, p252_decrypt_batch
+//   Error                           src/error.rs:11-44      -> p252_status
+// No permutation is ever computed on the host: without a CUDA device every batch call fails.
+#include <cuda_runtime.h>
+#include <nccl.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/poseidon252_b200.h"
+#include "host_field.h"
+#include "kernels.h"
+
+namespace {
+
+constexpr int kSlots = 3;                    // H2D / compute / D2H overlap for HOST buffers
+constexpr size_t kChunkItemsMax = 1 << 16;   // items per staged chunk (upper bound)
+constexpr size_t kChunkBytesTarget = 24u << 20;
+
+struct Slot {
+    cudaStream_t stream = nullptr;
+    void* arena = nullptr;
+    size_t arena_bytes = 0;
+};
+
+}  // namespace
+
+struct p252_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    Slot slots[kSlots];
+    cudaEvent_t ev_fork = nullptr;
+    cudaEvent_t ev_join[kSlots] = {nullptr, nullptr, nullptr};
+    uint64_t launches = 0;
+    std::string last_error;
+    // multi-GPU
+    ncclComm_t comm = nullptr;
+    int rank = 0, nranks = 1;
+    cudaStream_t comm_stream = nullptr;
+    cudaEvent_t ev_level = nullptr, ev_comm = nullptr;
+};
+
+namespace {
+
+struct DeviceGuard {
+    int prev = -1;
+    explicit DeviceGuard(int dev) {
+        cudaGetDevice(&prev);
+        if (prev != dev) cudaSetDevice(dev);
+    }
+    ~DeviceGuard() {
+        int cur = -1;
+        cudaGetDevice(&cur);
+        if (prev >= 0 && cur != prev) cudaSetDevice(prev);
+    }
+};
+
+int fail_cuda(p252_ctx* ctx, cudaError_t e, const char* where) {
+    if (ctx) ctx->last_error = std::string(where) + ": " + cudaGetErrorString(e);
+    cudaGetLastError();
+    return e == cudaErrorMemoryAllocation ? P252_ERR_OUT_OF_MEMORY : P252_ERR_CUDA;
+}
+int fail_nccl(p252_ctx* ctx, ncclResult_t e, const char* where) {
+    if (ctx) ctx->last_error = std::string(where) + ": " + ncclGetErrorString(e);
+    return P252_ERR_NCCL;
+}
+#define CU(call)                                              \
+    do {                                                      \
+        cudaError_t e__ = (call);                             \
+        if (e__ != cudaSuccess) return fail_cuda(ctx, e__, #call); \
+    } while (0)
+#define NC(call)                                              \
+    do {                                                      \
+        ncclResult_t e__ = (call);                            \
+        if (e__ != ncclSuccess) return fail_nccl(ctx, e__, #call); \
+    } while (0)
+
+bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+// One staged buffer of a HOST call.
+struct Io {
+    const void* h_in;    // copied to the device before the launch (may be null)
+    void* h_out;         // copied back after the launch (may be null)
+    size_t item_bytes;   // bytes per batch item
+};
+
+template <typename Launch>
+int run_host_pipeline(p252_ctx* ctx, std::vector<Io>& ios, size_t n, Launch launch) {
+    if (n == 0) return P252_OK;
+    size_t per_item = 0;
+    for (auto& io : ios) per_item += (io.item_bytes + 15) / 16 * 16;
+    size_t chunk = std::max<size_t>(1024, std::min(kChunkItemsMax, kChunkBytesTarget / std::max<size_t>(per_item, 1)));
+    chunk = (chunk + 127) / 128 * 128;
+    if (chunk > n) chunk = n;
+    // fork: slots wait for everything already enqueued on the context stream
+    CU(cudaEventRecord(ctx->ev_fork, ctx->stream));
+    for (int s = 0; s < kSlots; ++s) CU(cudaStreamWaitEvent(ctx->slots[s].stream, ctx->ev_fork, 0));
+    size_t k = 0;
+    for (size_t off = 0; off < n; off += chunk, ++k) {
+        const size_t cnt = std::min(chunk, n - off);
+        Slot& sl = ctx->slots[k % kSlots];
+        // arena layout: one 256-byte aligned region per buffer
+        size_t need = 0;
+        for (auto& io : ios) need += (chunk * io.item_bytes + 255) / 256 * 256;
+        if (sl.arena_bytes < need) {
+            CU(cudaStreamSynchronize(sl.stream));
+            if (sl.arena) CU(cudaFree(sl.arena));
+            sl.arena = nullptr;
+            sl.arena_bytes = 0;
+            CU(cudaMalloc(&sl.arena, need));
+            sl.arena_bytes = need;
+        }
+        std::vector<void*> d(ios.size());
+        size_t pos = 0;
+        for (size_t b = 0; b < ios.size(); ++b) {
+            d[b] = static_cast<uint8_t*>(sl.arena) + pos;
+            pos += (chunk * ios[b].item_bytes + 255) / 256 * 256;
+            if (ios[b].h_in)
+                CU(cudaMemcpyAsync(d[b], static_cast<const uint8_t*>(ios[b].h_in) + off * ios[b].item_bytes,
+                                   cnt * ios[b].item_bytes, cudaMemcpyHostToDevice, sl.stream));
+        }
+        cudaError_t le = launch(d.data(), cnt, sl.stream);
+        if (le != cudaSuccess) return fail_cuda(ctx, le, "kernel launch");
+        ctx->launches++;
+        for (size_t b = 0; b < ios.size(); ++b)
+            if (ios[b].h_out)
+                CU(cudaMemcpyAsync(static_cast<uint8_t*>(ios[b].h_out) + off * ios[b].item_bytes, d[b],
+                                   cnt * ios[b].item_bytes, cudaMemcpyDeviceToHost, sl.stream));
+    }
+    // join: the context stream continues after every slot
+    for (int s = 0; s < kSlots; ++s) {
+        CU(cudaEventRecord(ctx->ev_join[s], ctx->slots[s].stream));
+        CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_join[s], 0));
+    }
+    CU(cudaStreamSynchronize(ctx->stream));   // HOST calls are synchronous on return, like the reference
+    return P252_OK;
+}
+
+int finish_device_call(p252_ctx* ctx, cudaError_t le, int flags) {
+    if (le != cudaSuccess) return fail_cuda(ctx, le, "kernel launch");
+    ctx->launches++;
+    if (!(flags & P252_ASYNC)) CU(cudaStreamSynchronize(ctx->stream));
+    return P252_OK;
+}
+
+uint64_t domain_sep(int domain, bool* ok) {
+    *ok = true;
+    switch (domain) {
+        case P252_DOMAIN_MERKLE4: return 0x000000000000000fULL;      // src/hash.rs:47
+        case P252_DOMAIN_MERKLE2: return 0x0000000000000003ULL;      // src/hash.rs:49
+        case P252_DOMAIN_ENCRYPTION: return 0x0000000100000000ULL;   // src/hash.rs:51
+        case P252_DOMAIN_OTHER: return 0;                            // src/hash.rs:53
+    }
+    *ok = false;
+    return 0;
+}
+
+const uint64_t* limbs(const p252_fr* f) { return f->l; }
+
+}  // namespace
+
+extern "C" {
+
+const char* p252_version(void) { return "poseidon252_b200 0.1.0 (sm_100a)"; }
+
+const char* p252_strerror(int status) {
+    switch (status) {
+        case P252_OK: return "ok";
+        case P252_ERR_IO_PATTERN_VIOLATION: return "IOPatternViolation";
+        case P252_ERR_INVALID_IO_PATTERN: return "InvalidIOPattern";
+        case P252_ERR_TOO_FEW_INPUT_ELEMENTS: return "TooFewInputElements";
+        case P252_ERR_ENCRYPTION_FAILED: return "EncryptionFailed";
+        case P252_ERR_DECRYPTION_FAILED: return "DecryptionFailed";
+        case P252_ERR_INVALID_POINT: return "InvalidPoint";
+        case P252_ERR_INVALID_ARGUMENT: return "invalid argument";
+        case P252_ERR_CUDA: return "CUDA error";
+        case P252_ERR_NCCL: return "NCCL error";
+        case P252_ERR_NO_DEVICE: return "no usable sm_100 CUDA device (there is no CPU fallback)";
+        case P252_ERR_OUT_OF_MEMORY: return "out of device memory";
+    }
+    return "unknown status";
+}
+
+int p252_device_count(int* count) {
+    if (!count) return P252_ERR_INVALID_ARGUMENT;
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        n = 0;
+    }
+    *count = n;
+    return P252_OK;
+}
+
+int p252_create_on_stream(int device, void* cuda_stream, p252_ctx** out) {
+    if (!out) return P252_ERR_INVALID_ARGUMENT;
+    *out = nullptr;
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0) {
+        cudaGetLastError();
+        return P252_ERR_NO_DEVICE;
+    }
+    if (device < 0 || device >= n) return P252_ERR_INVALID_ARGUMENT;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return P252_ERR_NO_DEVICE;
+    if (prop.major != 10) return P252_ERR_NO_DEVICE;   // kernels are sm_100a SASS only
+    p252_ctx* ctx = new p252_ctx();
+    ctx->device = device;
+    DeviceGuard g(device);
+    auto bail = [&](cudaError_t e, const char* w) {
+        int rc = fail_cuda(nullptr, e, w);
+        p252_destroy(ctx);
+        return rc;
+    };
+    cudaError_t e;
+    if (cuda_stream) {
+        ctx->stream = static_cast<cudaStream_t>(cuda_stream);
+        ctx->own_stream = false;
+    } else {
+        if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess)
+            return bail(e, "cudaStreamCreate");
+        ctx->own_stream = true;
+    }
+    for (int s = 0; s < kSlots; ++s) {
+        if ((e = cudaStreamCreateWithFlags(&ctx->slots[s].stream, cudaStreamNonBlocking)) != cudaSuccess)
+            return bail(e, "cudaStreamCreate");
+        if ((e = cudaEventCreateWithFlags(&ctx->ev_join[s], cudaEventDisableTiming)) != cudaSuccess)
+            return bail(e, "cudaEventCreate");
+    }
+    if ((e = cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming)) != cudaSuccess)
+        return bail(e, "cudaEventCreate");
+    if ((e = cudaEventCreateWithFlags(&ctx->ev_level, cudaEventDisableTiming)) != cudaSuccess)
+        return bail(e, "cudaEventCreate");
+    if ((e = cudaEventCreateWithFlags(&ctx->ev_comm, cudaEventDisableTiming)) != cudaSuccess)
+        return bail(e, "cudaEventCreate");
+    *out = ctx;
+    return P252_OK;
+}
+
+int p252_create(int device, p252_ctx** out) { return p252_create_on_stream(device, nullptr, out); }
+
+void p252_destroy(p252_ctx* ctx) {
+    if (!ctx) return;
+    DeviceGuard g(ctx->device);
+    if (ctx->comm) ncclCommDestroy(ctx->comm);
+    if (ctx->comm_stream) cudaStreamDestroy(ctx->comm_stream);
+    for (int s = 0; s < kSlots; ++s) {
+        if (ctx->slots[s].stream) {
+            cudaStreamSynchronize(ctx->slots[s].stream);
+            cudaStreamDestroy(ctx->slots[s].stream);
+        }
+        if (ctx->slots[s].arena) cudaFree(ctx->slots[s].arena);
+        if (ctx->ev_join[s]) cudaEventDestroy(ctx->ev_join[s]);
+    }
+    if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
+    if (ctx->ev_level) cudaEventDestroy(ctx->ev_level);
+    if (ctx->ev_comm) cudaEventDestroy(ctx->ev_comm);
+    if (ctx->own_stream && ctx->stream) {
+        cudaStreamSynchronize(ctx->stream);
+        cudaStreamDestroy(ctx->stream);
+    }
+    delete ctx;
+}
+
+int p252_sync(p252_ctx* ctx) {
+    if (!ctx) return P252_ERR_INVALID_ARGUMENT;
+    DeviceGuard g(ctx->device);
+    CU(cudaStreamSynchronize(ctx->stream));
+    return P252_OK;
+}
+
+const char* p252_last_error(const p252_ctx* ctx) { return ctx ? ctx->last_error.c_str() : ""; }
+uint64_t p252_launch_count(const p252_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int p252_host_alloc(size_t bytes, void** out) {
+    if (!out) return P252_ERR_INVALID_ARGUMENT;
+    *out = nullptr;
+    p252_ctx* ctx = nullptr;
+    CU(cudaHostAlloc(out, bytes ? bytes : 1, cudaHostAllocPortable));
+    return P252_OK;
+}
+int p252_host_free(void* p) {
+    p252_ctx* ctx = nullptr;
+    if (p) CU(cudaFreeHost(p));
+    return P252_OK;
+}
+
+// ---- host-side sponge bookkeeping ---------------------------------------------------------------
+int p252_domain_separator(int domain, uint64_t* out) {
+    bool ok;
+    uint64_t v = domain_sep(domain, &ok);
+    if (!ok || !out) return P252_ERR_INVALID_ARGUMENT;
+    *out = v;
+    return P252_OK;
+}
+
+int p252_tag_input(const uint32_t* calls, size_t ncalls, uint64_t dsep, uint8_t* out, size_t* out_len) {
+    if (!calls || !out_len) return P252_ERR_INVALID_ARGUMENT;
+    // a valid io-pattern starts with an absorb, ends with a squeeze and has no zero-length call
+    if (ncalls == 0 || !(calls[0] & 0x80000000u) || (calls[ncalls - 1] & 0x80000000u)) return P252_ERR_INVALID_IO_PATTERN;
+    std::vector<uint32_t> words;
+    for (size_t i = 0; i < ncalls; ++i) {
+        if ((calls[i] & 0x7fffffffu) == 0) return P252_ERR_INVALID_IO_PATTERN;
+        if (!words.empty() && ((words.back() ^ calls[i]) & 0x80000000u) == 0)
+            words.back() += calls[i] & 0x7fffffffu;   // aggregate consecutive calls of one kind
+        else
+            words.push_back(calls[i]);
+    }
+    const size_t need = words.size() * 4 + 8;
+    if (!out || *out_len < need) {
+        *out_len = need;
+        return out ? P252_ERR_INVALID_ARGUMENT : P252_OK;
+    }
+    size_t p = 0;
+    for (uint32_t w : words)
+        for (int s = 24; s >= 0; s -= 8) out[p++] = (uint8_t)(w >> s);
+    for (int s = 56; s >= 0; s -= 8) out[p++] = (uint8_t)(dsep >> s);
+    *out_len = need;
+    return P252_OK;
+}
+
+int p252_hash_to_scalar(const uint8_t* bytes, size_t len, p252_fr* out) {
+    if (!out || (!bytes && len)) return P252_ERR_INVALID_ARGUMENT;
+    uint8_t digest[64];
+    p252::host::blake2b512(bytes, len, digest);
+    p252::host::from_bytes_wide(out->l, digest);
+    return P252_OK;
+}
+
+int p252_tag(const uint32_t* calls, size_t ncalls, uint64_t dsep, p252_fr* tag) {
+    if (!tag) return P252_ERR_INVALID_ARGUMENT;
+    std::vector<uint8_t> buf(ncalls * 4 + 8 + 8);
+    size_t len = buf.size();
+    int rc = p252_tag_input(calls, ncalls, dsep, buf.data(), &len);
+    if (rc != P252_OK) return rc;
+    return p252_hash_to_scalar(buf.data(), len, tag);
+}
+
+int p252_hash_tag(int domain, size_t in_len, size_t out_len, p252_fr* tag) {
+    bool ok;
+    const uint64_t dsep = domain_sep(domain, &ok);
+    if (!ok || !tag) return P252_ERR_INVALID_ARGUMENT;
+    // io_pattern, src/hash.rs:62-85
+    if (domain == P252_DOMAIN_MERKLE2 && (in_len != 2 || out_len != 1)) return P252_ERR_IO_PATTERN_VIOLATION;
+    if (domain == P252_DOMAIN_MERKLE4 && (in_len != 4 || out_len != 1)) return P252_ERR_IO_PATTERN_VIOLATION;
+    if (in_len == 0 || out_len == 0) return P252_ERR_INVALID_IO_PATTERN;
+    if (in_len >= 0x80000000ull || out_len >= 0x80000000ull) return P252_ERR_INVALID_ARGUMENT;
+    const uint32_t calls[2] = {0x80000000u | (uint32_t)in_len, (uint32_t)out_len};
+    return p252_tag(calls, 2, dsep, tag);
+}
+
+int p252_encryption_tag(size_t L, p252_fr* tag) {
+    if (!tag) return P252_ERR_INVALID_ARGUMENT;
+    if (L == 0) return P252_ERR_INVALID_IO_PATTERN;
+    if (L >= 0x7ffffff0ull) return P252_ERR_INVALID_ARGUMENT;
+    // [Absorb(2), Absorb(1), Squeeze(L), Absorb(L), Squeeze(1)], src/encryption.rs:67-73
+    const uint32_t calls[5] = {0x80000002u, 0x80000001u, (uint32_t)L, 0x80000000u | (uint32_t)L, 1u};
+    bool ok;
+    return p252_tag(calls, 5, domain_sep(P252_DOMAIN_ENCRYPTION, &ok), tag);
+}
+
+// ---- batch entry points ---------------------------------------------------------------------------
+static int permute_impl(p252_ctx* ctx, p252_fr* states, size_t n, int flags, bool dense) {
+    if (!ctx || (!states && n)) return P252_ERR_INVALID_ARGUMENT;
+    DeviceGuard g(ctx->device);
+    if (flags & P252_MEM_DEVICE) {
+        if (!aligned16(states)) return P252_ERR_INVALID_ARGUMENT;
+        if (n == 0) return P252_OK;
+        return finish_device_call(ctx, p252::launch_permute(states, n, dense, ctx->stream), flags);
+    }
+    std::vector<Io> ios = {{states, states, 160}};
+    return run_host_pipeline(ctx, ios, n, [&](void** d, size_t cnt, cudaStream_t st) {
+        return p252::launch_permute(d[0], cnt, dense, st);
+    });
+}
+
+int p252_permute_batch(p252_ctx* ctx, p252_fr* states, size_t n, int flags) {
+    return permute_impl(ctx, states, n, flags, false);
+}
+int p252_permute_batch_dense(p252_ctx* ctx, p252_fr* states, size_t n, int flags) {
+    return permute_impl(ctx, states, n, flags, true);
+}
+
+int p252_digest_batch(p252_ctx* ctx, const p252_fr* tag, const p252_fr* in, size_t n, size_t in_len, p252_fr* out,
+                      size_t out_len, int flags) {
+    if (!ctx || !tag || ((!in || !out) && n)) return P252_ERR_INVALID_ARGUMENT;
+    if (in_len == 0 || out_len == 0) return P252_ERR_INVALID_IO_PATTERN;
+    if (in_len > 0x7fffffffull / 32 || out_len > 0x7fffffffull / 32) return P252_ERR_INVALID_ARGUMENT;
+    DeviceGuard g(ctx->device);
+    const uint32_t il = (uint32_t)in_len, ol = (uint32_t)out_len;
+    if (flags & P252_MEM_DEVICE) {
+        if (!aligned16(in) || !aligned16(out)) return P252_ERR_INVALID_ARGUMENT;
+        if (n == 0) return P252_OK;
+        return finish_device_call(ctx, p252::launch_digest(limbs(tag), in, n, il, out, ol, ctx->stream), flags);
+    }
+    std::vector<Io> ios = {{in, nullptr, in_len * 32}, {nullptr, out, out_len * 32}};
+    return run_host_pipeline(ctx, ios, n, [&](void** d, size_t cnt, cudaStream_t st) {
+        return p252::launch_digest(limbs(tag), d[0], cnt, il, d[1], ol, st);
+    });
+}
+
+int p252_hash_batch(p252_ctx* ctx, int domain, const p252_fr* in, size_t n, size_t in_len, p252_fr* out,
+                    size_t out_len, int flags) {
+    p252_fr tag;
+    int rc = p252_hash_tag(domain, in_len, out_len, &tag);
+    if (rc != P252_OK) return rc;
+    return p252_digest_batch(ctx, &tag, in, n, in_len, out, out_len, flags);
+}
+
+int p252_encrypt_batch(p252_ctx* ctx, const p252_fr* msg, size_t n, size_t L, const p252_fr* secret_uv,
+                       const p252_fr* nonce, p252_fr* cipher, int flags) {
+    if (!ctx || ((!msg || !secret_uv || !nonce || !cipher) && n)) return P252_ERR_INVALID_ARGUMENT;
+    p252_fr tag;
+    int rc = p252_encryption_tag(L, &tag);
+    if (rc != P252_OK) return rc;
+    DeviceGuard g(ctx->device);
+    const uint32_t l32 = (uint32_t)L;
+    if (flags & P252_MEM_DEVICE) {
+        if (!aligned16(msg) || !aligned16(secret_uv) || !aligned16(nonce) || !aligned16(cipher))
+            return P252_ERR_INVALID_ARGUMENT;
+        if (n == 0) return P252_OK;
+        return finish_device_call(
+            ctx, p252::launch_encrypt(limbs(&tag), msg, n, l32, secret_uv, nonce, cipher, ctx->stream), flags);
+    }
+    std::vector<Io> ios = {{msg, nullptr, L * 32}, {secret_uv, nullptr, 64}, {nonce, nullptr, 32},
+                           {nullptr, cipher, (L + 1) * 32}};
+    return run_host_pipeline(ctx, ios, n, [&](void** d, size_t cnt, cudaStream_t st) {
+        return p252::launch_encrypt(limbs(&tag), d[0], cnt, l32, d[1], d[2], d[3], st);
+    });
+}
+
+int p252_decrypt_batch(p252_ctx* ctx, const p252_fr* cipher, size_t n, size_t L, const p252_fr* secret_uv,
+                       const p252_fr* nonce, p252_fr* msg, uint8_t* ok, size_t* n_failed, int flags) {
+    if (!ctx || ((!cipher || !secret_uv || !nonce || !msg || !ok) && n)) return P252_ERR_INVALID_ARGUMENT;
+    p252_fr tag;
+    int rc = p252_encryption_tag(L, &tag);
+    if (rc != P252_OK) return rc;
+    DeviceGuard g(ctx->device);
+    const uint32_t l32 = (uint32_t)L;
+    if (flags & P252_MEM_DEVICE) {
+        if (!aligned16(cipher) || !aligned16(secret_uv) || !aligned16(nonce) || !aligned16(msg))
+            return P252_ERR_INVALID_ARGUMENT;
+        if (n_failed) *n_failed = 0;   // not computed for device buffers (ok[] stays on the device)
+        if (n == 0) return P252_OK;
+        return finish_device_call(
+            ctx, p252::launch_decrypt(limbs(&tag), cipher, n, l32, secret_uv, nonce, msg, ok, ctx->stream), flags);
+    }
+    std::vector<Io> ios = {{cipher, nullptr, (L + 1) * 32}, {secret_uv, nullptr, 64}, {nonce, nullptr, 32},
+                           {nullptr, msg, L * 32}, {nullptr, ok, 1}};
+    rc = run_host_pipeline(ctx, ios, n, [&](void** d, size_t cnt, cudaStream_t st) {
+        return p252::launch_decrypt(limbs(&tag), d[0], cnt, l32, d[1], d[2], d[3], static_cast<uint8_t*>(d[4]), st);
+    });
+    if (rc == P252_OK && n_failed) {
+        size_t bad = 0;
+        for (size_t i = 0; i < n; ++i) bad += ok[i] ? 0 : 1;
+        *n_failed = bad;
+    }
+    return rc;
+}
+
+// ---- arity-4 Merkle tree ------------------------------------------------------------------------------
+int p252_merkle4_level(p252_ctx* ctx, const p252_fr* children, size_t n_parents, p252_fr* parents, int flags) {
+    return p252_hash_batch(ctx, P252_DOMAIN_MERKLE4, children, n_parents, 4, parents, 1, flags);
+}
+
+int p252_merkle4_tree_nodes(size_t n_leaves, size_t* n_internal, int* n_levels) {
+    size_t m = n_leaves;
+    int lv = 0;
+    if (m == 0) return P252_ERR_INVALID_ARGUMENT;
+    while (m > 1) {
+        if (m % 4) return P252_ERR_IO_PATTERN_VIOLATION;   // a level that is not a multiple of the arity
+        m /= 4;
+        ++lv;
+    }
+    if (lv == 0) return P252_ERR_INVALID_ARGUMENT;
+    if (n_internal) *n_internal = (n_leaves - 1) / 3;
+    if (n_levels) *n_levels = lv;
+    return P252_OK;
+}
+
+static int merkle4_build_device(p252_ctx* ctx, const p252_fr* leaves, size_t n_leaves, p252_fr* nodes) {
+    p252_fr tag;
+    int rc = p252_hash_tag(P252_DOMAIN_MERKLE4, 4, 1, &tag);
+    if (rc != P252_OK) return rc;
+    const p252_fr* src = leaves;
+    p252_fr* dst = nodes;
+    for (size_t m = n_leaves / 4; m >= 1; m /= 4) {
+        cudaError_t le = p252::launch_digest(limbs(&tag), src, m, 4, dst, 1, ctx->stream);
+        if (le != cudaSuccess) return fail_cuda(ctx, le, "kernel launch");
+        ctx->launches++;
+        src = dst;
+        dst += m;
+        if (m == 1) break;
+    }
+    return P252_OK;
+}
+
+int p252_merkle4_build(p252_ctx* ctx, const p252_fr* leaves, size_t n_leaves, p252_fr* nodes_out, int flags) {
+    if (!ctx || !leaves || !nodes_out) return P252_ERR_INVALID_ARGUMENT;
+    size_t n_internal;
+    int rc = p252_merkle4_tree_nodes(n_leaves, &n_internal, nullptr);
+    if (rc != P252_OK) return rc;
+    DeviceGuard g(ctx->device);
+    if (flags & P252_MEM_DEVICE) {
+        if (!aligned16(leaves) || !aligned16(nodes_out)) return P252_ERR_INVALID_ARGUMENT;
+        rc = merkle4_build_device(ctx, leaves, n_leaves, nodes_out);
+        if (rc != P252_OK) return rc;
+        if (!(flags & P252_ASYNC)) CU(cudaStreamSynchronize(ctx->stream));
+        return P252_OK;
+    }
+    // HOST: the first (largest) level streams through the chunked pipeline straight from the host
+    // leaves; the remaining levels (1/4 of the work) run on the device-resident level.
+    p252_fr* d_nodes = nullptr;
+    CU(cudaMalloc(reinterpret_cast<void**>(&d_nodes), n_internal * sizeof(p252_fr)));
+    p252_fr tag;
+    p252_hash_tag(P252_DOMAIN_MERKLE4, 4, 1, &tag);
+    {
+        std::vector<Io> ios = {{leaves, nullptr, 128}, {nullptr, nodes_out, 32}};
+        size_t done = 0;   // the pipeline hands chunks in order; mirror each chunk into d_nodes as well
+        rc = run_host_pipeline(ctx, ios, n_leaves / 4, [&](void** d, size_t cnt, cudaStream_t st) {
+            cudaError_t e = p252::launch_digest(limbs(&tag), d[0], cnt, 4, d[1], 1, st);
+            if (e != cudaSuccess) return e;
+            e = cudaMemcpyAsync(d_nodes + done, d[1], cnt * sizeof(p252_fr), cudaMemcpyDeviceToDevice, st);
+            done += cnt;
+            return e;
+        });
+    }
+    if (rc == P252_OK && n_leaves > 4) {
+        rc = merkle4_build_device(ctx, d_nodes, n_leaves / 4, d_nodes + n_leaves / 4);
+        if (rc == P252_OK) {
+            cudaError_t e = cudaMemcpyAsync(nodes_out + n_leaves / 4, d_nodes + n_leaves / 4,
+                                            (n_internal - n_leaves / 4) * sizeof(p252_fr), cudaMemcpyDeviceToHost,
+                                            ctx->stream);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+            if (e != cudaSuccess) rc = fail_cuda(ctx, e, "merkle4 D2H");
+        }
+    }
+    cudaFree(d_nodes);
+    return rc;
+}
+
+// ---- multi-GPU ------------------------------------------------------------------------------------------
+int p252_dist_unique_id(uint8_t id[P252_NCCL_UNIQUE_ID_BYTES]) {
+    static_assert(sizeof(ncclUniqueId) <= P252_NCCL_UNIQUE_ID_BYTES, "unique id size");
+    p252_ctx* ctx = nullptr;
+    if (!id) return P252_ERR_INVALID_ARGUMENT;
+    ncclUniqueId u;
+    NC(ncclGetUniqueId(&u));
+    memset(id, 0, P252_NCCL_UNIQUE_ID_BYTES);
+    memcpy(id, &u, sizeof u);
+    return P252_OK;
+}
+
+int p252_dist_init(p252_ctx* ctx, const uint8_t id[P252_NCCL_UNIQUE_ID_BYTES], int rank, int nranks) {
+    if (!ctx || !id || nranks < 1 || rank < 0 || rank >= nranks) return P252_ERR_INVALID_ARGUMENT;
+    if (ctx->comm) return P252_ERR_INVALID_ARGUMENT;
+    DeviceGuard g(ctx->device);
+    ncclUniqueId u;
+    memcpy(&u, id, sizeof u);
+    NC(ncclCommInitRank(&ctx->comm, nranks, u, rank));
+    ctx->rank = rank;
+    ctx->nranks = nranks;
+    CU(cudaStreamCreateWithFlags(&ctx->comm_stream, cudaStreamNonBlocking));
+    return P252_OK;
+}
+
+int p252_dist_finalize(p252_ctx* ctx) {
+    if (!ctx) return P252_ERR_INVALID_ARGUMENT;
+    DeviceGuard g(ctx->device);
+    if (ctx->comm) {
+        CU(cudaStreamSynchronize(ctx->comm_stream));
+        NC(ncclCommDestroy(ctx->comm));
+        ctx->comm = nullptr;
+    }
+    if (ctx->comm_stream) {
+        cudaStreamDestroy(ctx->comm_stream);
+        ctx->comm_stream = nullptr;
+    }
+    ctx->rank = 0;
+    ctx->nranks = 1;
+    return P252_OK;
+}
+
+// Contiguous sharding: rank r owns nodes [r*M/G, (r+1)*M/G) of every level with M >= G nodes, whose
+// children are exactly rank r's slice of the level below -- so the compute stream climbs its own
+// subtree without waiting, while the all-gather of each finished level (the level's replication to
+// all GPUs over NVLink) runs on a second stream.  Levels with M < G nodes are computed redundantly
+// by every rank from the gathered level below.
+int p252_merkle4_build_dist(p252_ctx* ctx, const p252_fr* leaves_shard, size_t n_leaves_total, p252_fr* nodes_out,
+                            int flags) {
+    if (!ctx || !leaves_shard || !nodes_out) return P252_ERR_INVALID_ARGUMENT;
+    if (!(flags & P252_MEM_DEVICE)) return P252_ERR_INVALID_ARGUMENT;   // shards live on the GPU
+    if (!aligned16(leaves_shard) || !aligned16(nodes_out)) return P252_ERR_INVALID_ARGUMENT;
+    size_t n_internal;
+    int rc = p252_merkle4_tree_nodes(n_leaves_total, &n_internal, nullptr);
+    if (rc != P252_OK) return rc;
+    const int G = ctx->nranks, r = ctx->rank;
+    if (G > 1 && !ctx->comm) return P252_ERR_INVALID_ARGUMENT;
+    if (n_leaves_total % (size_t)G || (n_leaves_total / G) % 4) return P252_ERR_INVALID_ARGUMENT;
+    DeviceGuard g(ctx->device);
+    p252_fr tag;
+    p252_hash_tag(P252_DOMAIN_MERKLE4, 4, 1, &tag);
+
+    const p252_fr* below_full = nullptr;   // complete level below (valid once gathered)
+    const p252_fr* below_mine = leaves_shard;   // this rank's slice of the level below
+    p252_fr* level = nodes_out;
+    bool gathered_below = true;   // leaves: only the shard is ever needed
+    CU(cudaEventRecord(ctx->ev_comm, ctx->stream));
+    for (size_t m = n_leaves_total / 4;; m /= 4) {
+        if (m % (size_t)G == 0) {
+            const size_t cnt = m / G;
+            cudaError_t le = p252::launch_digest(limbs(&tag), below_mine, cnt, 4, level + (size_t)r * cnt, 1, ctx->stream);
+            if (le != cudaSuccess) return fail_cuda(ctx, le, "kernel launch");
+            ctx->launches++;
+            if (G > 1) {
+                CU(cudaEventRecord(ctx->ev_level, ctx->stream));
+                CU(cudaStreamWaitEvent(ctx->comm_stream, ctx->ev_level, 0));
+                NC(ncclAllGather(level + (size_t)r * cnt, level, cnt * 4, ncclUint64, ctx->comm, ctx->comm_stream));
+                CU(cudaEventRecord(ctx->ev_comm, ctx->comm_stream));
+                gathered_below = false;   // in flight
+            }
+            below_mine = level + (size_t)r * cnt;
+        } else {
+            // small level: needs the complete level below on this rank
+            if (!gathered_below) {
+                CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_comm, 0));
+                gathered_below = true;
+            }
+            cudaError_t le = p252::launch_digest(limbs(&tag), below_full, m, 4, level, 1, ctx->stream);
+            if (le != cudaSuccess) return fail_cuda(ctx, le, "kernel launch");
+            ctx->launches++;
+            below_mine = level;   // unused from here on
+        }
+        below_full = level;
+        level += m;
+        if (m == 1) break;
+    }
+    // every level must be complete on every rank before the call is considered done
+    CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_comm, 0));
+    if (!(flags & P252_ASYNC)) CU(cudaStreamSynchronize(ctx->stream));
+    return P252_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,316 @@
+// Batch kernels of the B200 Poseidon/Hades engine (sm_100a).  One sponge state per thread, state in
+// registers; global memory is touched only by 128-bit accesses: warp-cooperative, fully coalesced
+// tiles staged through shared memory for the hash/permute kernels (each LDG.128/STG.128 of a warp
+// covers whole 128-byte item chunks), per-thread 2 x 128-bit per scalar for encrypt/decrypt.
+//
+// Sponge schedule = dusk-safe 0.3 `Sponge` as driven by the reference:
+//   Hash::finalize   /root/reference/src/hash.rs:128-155      -> k_sponge_digest
+//   encrypt/decrypt  /root/reference/src/encryption.rs:62-95  -> k_encrypt / k_decrypt
+//   Safe::permute    /root/reference/src/hades/permutation/scalar.rs:25-27 -> k_permute
+// capacity = state[0] = tag, rate = state[1..5]; absorb adds into state[pos+1] and permutes when
+// pos == 4; any absorb forces a permutation before the next squeeze.
+#include "kernels.h"
+
+#include "hades_device.cuh"
+
+namespace p252 {
+
+constexpr int kThreads = 128;
+constexpr int kWarps = kThreads / 32;
+
+struct FrArg {
+    uint32_t l[8];
+};
+
+__device__ __forceinline__ uint4 ldg128(const void* p) { return __ldg(reinterpret_cast<const uint4*>(p)); }
+
+// ---- warp-cooperative 128-byte-chunk gather / scatter -------------------------------------------
+// 32 items, one per lane; item k's chunk lives at base + k*stride (stride multiple of 32 B).
+// Global side: lane l moves 16 B; 8 consecutive lanes cover one item's 128-byte chunk, so every
+// LDG.128 / STG.128 of the warp touches 4 complete 128-byte segments.  Shared side: XOR swizzle on
+// the 16-byte column keeps both the row-wise (global side) and the item-per-lane (register side)
+// accesses bank-conflict free.
+__device__ __forceinline__ void warp_gather(uint4 (*st)[8], const uint8_t* base, size_t stride, int nitems,
+                                            int nscal, int lane, uint32_t (&v)[4][8]) {
+    const int part = lane & 7;
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+        const int item = r * 4 + (lane >> 3);
+        uint4 x = make_uint4(0, 0, 0, 0);
+        if (item < nitems && (part >> 1) < nscal) x = ldg128(base + (size_t)item * stride + part * 16);
+        st[item][part ^ (item & 7)] = x;
+    }
+    __syncwarp();
+#pragma unroll
+    for (int p = 0; p < 8; ++p) {
+        const uint4 x = st[lane][p ^ (lane & 7)];
+        v[p >> 1][(p & 1) * 4 + 0] = x.x;
+        v[p >> 1][(p & 1) * 4 + 1] = x.y;
+        v[p >> 1][(p & 1) * 4 + 2] = x.z;
+        v[p >> 1][(p & 1) * 4 + 3] = x.w;
+    }
+    __syncwarp();
+}
+
+__device__ __forceinline__ void warp_scatter(uint4 (*st)[8], uint8_t* base, size_t stride, int nitems, int nscal,
+                                             int lane, const uint32_t (&v)[4][8]) {
+#pragma unroll
+    for (int p = 0; p < 8; ++p)
+        st[lane][p ^ (lane & 7)] = make_uint4(v[p >> 1][(p & 1) * 4 + 0], v[p >> 1][(p & 1) * 4 + 1],
+                                              v[p >> 1][(p & 1) * 4 + 2], v[p >> 1][(p & 1) * 4 + 3]);
+    __syncwarp();
+    const int part = lane & 7;
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+        const int item = r * 4 + (lane >> 3);
+        if (item < nitems && (part >> 1) < nscal)
+            *reinterpret_cast<uint4*>(base + (size_t)item * stride + part * 16) = st[item][part ^ (item & 7)];
+    }
+    __syncwarp();
+}
+
+// ---- Hash::digest-shaped sponge: Absorb(in_len) -> Squeeze(out_len), item-major AoS ------------
+// One permutation call site: step s > 0 is always preceded by a permutation; steps [0, nin) absorb
+// 4-scalar chunks, steps [nin, nin+nout) squeeze 4-scalar chunks.  Permutations = nin + nout - 1
+// = ceil(in_len/4) + ceil(out_len/4) - 1  (Merkle4: exactly 1).
+__global__ void __launch_bounds__(kThreads) k_sponge_digest(FrArg tag, const uint8_t* __restrict__ in, size_t n,
+                                                            uint32_t in_len, uint8_t* __restrict__ out,
+                                                            uint32_t out_len) {
+    __shared__ uint4 stage[kWarps][32][8];
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const size_t item0 = ((size_t)blockIdx.x * kWarps + warp) * 32;
+    if (item0 >= n) return;
+    const int nitems = (n - item0 < 32) ? (int)(n - item0) : 32;
+    uint4(*st)[8] = stage[warp];
+
+    uint32_t s[5][8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        s[0][k] = tag.l[k];
+        s[1][k] = s[2][k] = s[3][k] = s[4][k] = 0;
+    }
+    const uint32_t nin = (in_len + 3) / 4, nout = (out_len + 3) / 4;
+    const uint8_t* in_w = in + item0 * (size_t)in_len * 32;
+    uint8_t* out_w = out + item0 * (size_t)out_len * 32;
+#pragma unroll 1
+    for (uint32_t step = 0; step < nin + nout; ++step) {
+        if (step > 0) hades_permute(s);
+        if (step < nin) {
+            const uint32_t left = in_len - 4 * step;
+            const int nscal = left < 4 ? (int)left : 4;
+            uint32_t v[4][8];
+            warp_gather(st, in_w + (size_t)step * 128, (size_t)in_len * 32, nitems, nscal, lane, v);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                if (q < nscal) {
+                    uint32_t t[8];
+                    fr_add_mod(t, s[1 + q], v[q]);
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) s[1 + q][k] = t[k];
+                }
+            }
+        } else {
+            const uint32_t c = step - nin;
+            const uint32_t left = out_len - 4 * c;
+            const int nscal = left < 4 ? (int)left : 4;
+            uint32_t v[4][8];
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+#pragma unroll
+                for (int k = 0; k < 8; ++k) v[q][k] = s[1 + q][k];
+            warp_scatter(st, out_w + (size_t)c * 128, (size_t)out_len * 32, nitems, nscal, lane, v);
+        }
+    }
+}
+
+// ---- raw permutation of n x 5 states in place (Safe::permute) -----------------------------------
+template <bool kDense>
+__global__ void __launch_bounds__(kThreads) k_permute(uint8_t* __restrict__ states, size_t n) {
+    __shared__ uint4 stage[kWarps][32][8];
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const size_t item0 = ((size_t)blockIdx.x * kWarps + warp) * 32;
+    if (item0 >= n) return;
+    const int nitems = (n - item0 < 32) ? (int)(n - item0) : 32;
+    uint4(*st)[8] = stage[warp];
+    uint8_t* base = states + item0 * 160;
+
+    uint32_t s[5][8];
+    {
+        uint32_t v[4][8];
+        warp_gather(st, base, 160, nitems, 4, lane, v);
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+#pragma unroll
+            for (int k = 0; k < 8; ++k) s[q][k] = v[q][k];
+        warp_gather(st, base + 128, 160, nitems, 1, lane, v);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) s[4][k] = v[0][k];
+    }
+    if (kDense)
+        dense_permute(s);
+    else
+        hades_permute(s);
+    {
+        uint32_t v[4][8];
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+#pragma unroll
+            for (int k = 0; k < 8; ++k) v[q][k] = s[q][k];
+        warp_scatter(st, base, 160, nitems, 4, lane, v);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) v[0][k] = s[4][k];
+        warp_scatter(st, base + 128, 160, nitems, 1, lane, v);
+    }
+}
+
+// ---- encrypt / decrypt (dusk_safe::encrypt / decrypt with Domain::Encryption) -------------------
+// pattern [Absorb(2), Absorb(1), Squeeze(L), Absorb(L), Squeeze(1)]; 2*ceil(L/4) permutations.
+__device__ __forceinline__ void load_fr(uint32_t (&d)[8], const uint8_t* p) {
+    const uint4 a = ldg128(p), b = ldg128(p + 16);
+    d[0] = a.x, d[1] = a.y, d[2] = a.z, d[3] = a.w;
+    d[4] = b.x, d[5] = b.y, d[6] = b.z, d[7] = b.w;
+}
+__device__ __forceinline__ void load_fr_rw(uint32_t (&d)[8], const uint8_t* p) {   // coherent (own stores)
+    const uint4 a = *reinterpret_cast<const uint4*>(p), b = *reinterpret_cast<const uint4*>(p + 16);
+    d[0] = a.x, d[1] = a.y, d[2] = a.z, d[3] = a.w;
+    d[4] = b.x, d[5] = b.y, d[6] = b.z, d[7] = b.w;
+}
+__device__ __forceinline__ void store_fr(uint8_t* p, const uint32_t (&d)[8]) {
+    *reinterpret_cast<uint4*>(p) = make_uint4(d[0], d[1], d[2], d[3]);
+    *reinterpret_cast<uint4*>(p + 16) = make_uint4(d[4], d[5], d[6], d[7]);
+}
+
+template <bool kDecrypt>
+__global__ void __launch_bounds__(kThreads) k_crypt(FrArg tag, const uint8_t* __restrict__ src, size_t n, uint32_t L,
+                                                    const uint8_t* __restrict__ secret_uv,
+                                                    const uint8_t* __restrict__ nonce, uint8_t* dst,
+                                                    uint8_t* __restrict__ ok) {
+    const size_t i = (size_t)blockIdx.x * kThreads + threadIdx.x;
+    if (i >= n) return;
+    // encrypt: src = message (n x L), dst = cipher (n x (L+1)); decrypt: the other way round
+    const size_t src_len = kDecrypt ? (size_t)L + 1 : L, dst_len = kDecrypt ? L : (size_t)L + 1;
+    const uint8_t* srci = src + i * src_len * 32;
+    uint8_t* dsti = dst + i * dst_len * 32;
+    const uint8_t* msgi = kDecrypt ? dsti : srci;        // the plaintext, wherever it lives
+
+    uint32_t s[5][8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) s[0][k] = tag.l[k], s[4][k] = 0;
+    load_fr(s[1], secret_uv + i * 64);                   // Absorb(2): u, v added to zero
+    load_fr(s[2], secret_uv + i * 64 + 32);
+    load_fr(s[3], nonce + i * 32);                       // Absorb(1)
+    const uint32_t nk = (L + 3) / 4;
+    bool good = true;
+#pragma unroll 1
+    for (uint32_t step = 0; step < 2 * nk; ++step) {
+        hades_permute(s);
+        if (step < nk) {
+            // Squeeze chunk `step` of the keystream and emit cipher (or recovered message)
+            const uint32_t left = L - 4 * step;
+            const int nscal = left < 4 ? (int)left : 4;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                if (q < nscal) {
+                    uint32_t x[8], y[8];
+                    load_fr(x, srci + (size_t)(4 * step + q) * 32);
+                    if (kDecrypt)
+                        fr_sub_mod(y, x, s[1 + q]);      // Encryption::subtract
+                    else
+                        fr_add_mod(y, x, s[1 + q]);      // Safe::add
+                    store_fr(dsti + (size_t)(4 * step + q) * 32, y);
+                }
+            }
+        }
+        if (step + 1 >= nk && step + 1 < 2 * nk) {
+            // Absorb(L) chunk c of the plaintext: chunk 0 right after the last squeeze (no
+            // permutation in between), chunk c > 0 after one more permutation each
+            const uint32_t c = step + 1 - nk;
+            const uint32_t left = L - 4 * c;
+            const int nscal = left < 4 ? (int)left : 4;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                if (q < nscal) {
+                    uint32_t x[8], t[8];
+                    if (kDecrypt)
+                        load_fr_rw(x, msgi + (size_t)(4 * c + q) * 32);
+                    else
+                        load_fr(x, msgi + (size_t)(4 * c + q) * 32);
+                    fr_add_mod(t, s[1 + q], x);
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) s[1 + q][k] = t[k];
+                }
+            }
+        }
+        if (step + 1 == 2 * nk) {
+            // Squeeze(1): authentication element
+            if (kDecrypt) {
+                uint32_t x[8];
+                load_fr(x, srci + (size_t)L * 32);
+#pragma unroll
+                for (int k = 0; k < 8; ++k) good = good && (x[k] == s[1][k]);   // Encryption::is_equal
+            } else {
+                store_fr(dsti + (size_t)L * 32, s[1]);
+            }
+        }
+    }
+    if (kDecrypt) {
+        ok[i] = good ? 1 : 0;
+        if (!good) {                                      // Error::DecryptionFailed: release nothing
+            const uint32_t zero[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+            for (uint32_t k = 0; k < L; ++k) store_fr(dsti + (size_t)k * 32, zero);
+        }
+    }
+}
+
+// ---- host-callable launchers -------------------------------------------------------------------
+static inline FrArg to_arg(const uint64_t tag[4]) {
+    FrArg a;
+    for (int k = 0; k < 4; ++k) {
+        a.l[2 * k] = (uint32_t)tag[k];
+        a.l[2 * k + 1] = (uint32_t)(tag[k] >> 32);
+    }
+    return a;
+}
+
+static inline unsigned grid_for(size_t n) { return (unsigned)((n + kThreads - 1) / kThreads); }
+
+cudaError_t launch_permute(void* states, size_t n, bool dense, cudaStream_t st) {
+    if (n == 0) return cudaSuccess;
+    if (dense)
+        k_permute<true><<<grid_for(n), kThreads, 0, st>>>(static_cast<uint8_t*>(states), n);
+    else
+        k_permute<false><<<grid_for(n), kThreads, 0, st>>>(static_cast<uint8_t*>(states), n);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_digest(const uint64_t tag[4], const void* in, size_t n, uint32_t in_len, void* out,
+                          uint32_t out_len, cudaStream_t st) {
+    if (n == 0) return cudaSuccess;
+    k_sponge_digest<<<grid_for(n), kThreads, 0, st>>>(to_arg(tag), static_cast<const uint8_t*>(in), n, in_len,
+                                                      static_cast<uint8_t*>(out), out_len);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_encrypt(const uint64_t tag[4], const void* msg, size_t n, uint32_t L, const void* secret_uv,
+                           const void* nonce, void* cipher, cudaStream_t st) {
+    if (n == 0) return cudaSuccess;
+    k_crypt<false><<<grid_for(n), kThreads, 0, st>>>(to_arg(tag), static_cast<const uint8_t*>(msg), n, L,
+                                                     static_cast<const uint8_t*>(secret_uv),
+                                                     static_cast<const uint8_t*>(nonce),
+                                                     static_cast<uint8_t*>(cipher), nullptr);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_decrypt(const uint64_t tag[4], const void* cipher, size_t n, uint32_t L, const void* secret_uv,
+                           const void* nonce, void* msg, uint8_t* ok, cudaStream_t st) {
+    if (n == 0) return cudaSuccess;
+    k_crypt<true><<<grid_for(n), kThreads, 0, st>>>(to_arg(tag), static_cast<const uint8_t*>(cipher), n, L,
+                                                    static_cast<const uint8_t*>(secret_uv),
+                                                    static_cast<const uint8_t*>(nonce), static_cast<uint8_t*>(msg),
+                                                    ok);
+    return cudaGetLastError();
+}
+
+}  // namespace p252

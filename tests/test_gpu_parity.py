@@ -1,0 +1,253 @@
+"""GPU (-m gpu): the CUDA path, called through the C ABI, is bit-exact against the oracle, the
+reference's KATs and the committed golden vectors; edge cases; full-size properties."""
+import numpy as np
+import pytest
+
+import poseidon252_b200 as pb
+from conftest import edge_and_random_scalars, hx, mont, unmont
+from poseidon252_b200 import hash as H
+from poseidon252_b200.scalar import random_limbs_fast, random_scalars
+
+pytestmark = pytest.mark.gpu
+
+
+def _tag(oracle, pattern, dom):
+    return mont(oracle.hash_to_scalar(oracle.tag_input(pattern, dom)))
+
+
+# ---- permutation -------------------------------------------------------------------------------
+def test_permute_golden(engine, golden):
+    ins = mont([[hx(s) for s in e["in"]] for e in golden["perm"]])
+    out = engine.permute_batch(ins)
+    for row, e in zip(out, golden["perm"]):
+        assert ["0x%064x" % v for v in unmont(row)] == e["out"]
+    dense = engine.permute_batch(ins, dense=True)
+    assert np.array_equal(out, dense)
+
+
+@pytest.mark.parametrize("n", [1, 2, 31, 32, 33, 127, 128, 129, 1000, 4099])
+def test_permute_vs_oracle_ragged(engine, coracle, n):
+    rng = np.random.default_rng(n)
+    states = edge_and_random_scalars(rng, n * 5).reshape(n, 5, 4)
+    want = coracle.permute(states)
+    got = engine.permute_batch(states)
+    assert np.array_equal(got, want)
+    assert np.array_equal(engine.permute_batch(states, dense=True), want)
+
+
+def test_permute_empty_and_inplace(engine):
+    z = np.zeros((0, 5, 4), dtype=np.uint64)
+    assert engine.permute_batch(z).shape == (0, 5, 4)
+    s = random_scalars(np.random.default_rng(1), (10, 5))
+    t = s.copy()
+    engine.permute_batch_inplace(t)
+    assert np.array_equal(t, engine.permute_batch(s))
+    # hades_det, src/hades/permutation/scalar.rs:86-98
+    x = pb.hades.permute(mont([17] * 5), engine)
+    y = pb.hades.permute(mont([17] * 5), engine)
+    z = pb.hades.permute(mont([19] * 5), engine)
+    assert np.array_equal(x, y) and not np.array_equal(x, z)
+
+
+def test_permute_device_tensors(engine, coracle):
+    import torch
+    rng = np.random.default_rng(11)
+    states = random_scalars(rng, (777, 5))
+    d = torch.from_numpy(states.view(np.int64)).cuda()
+    out = engine.permute_batch(d)
+    assert out.is_cuda and np.array_equal(out.cpu().numpy().view(np.uint64), coracle.permute(states))
+
+
+# ---- reference KATs through the GPU sponge -----------------------------------------------------------
+def test_reference_kats_on_gpu(engine, oracle):
+    """src/hades.rs:128-162: tag 0, Absorb(n) + Absorb(1) of one, Squeeze(1).  Two absorbs aggregate
+    into one run of n+1 elements in the sponge schedule."""
+    kin = oracle.kat_inputs()
+    for n, want in oracle.KAT_EXPECTED.items():
+        data = mont(kin[:n] + [1]).reshape(1, n + 1, 4)
+        out = engine.digest_batch_with_tag(mont(0), data, 1)
+        assert oracle.debug_hex(unmont(out)[0, 0]) == want
+
+
+# ---- Hash --------------------------------------------------------------------------------------
+def test_digest_golden(engine, golden):
+    for e in golden["digest"]:
+        dom = {0xF: pb.Domain.Merkle4, 0x3: pb.Domain.Merkle2, 0: pb.Domain.Other}[e["domain"]]
+        h = pb.Hash(dom, engine)
+        h.output_len(e["out_len"])
+        h.update(mont([hx(s) for s in e["in"]]))
+        assert ["0x%064x" % v for v in unmont(h.finalize())] == e["out"]
+
+
+def test_readme_example(engine, oracle):
+    """README.md:22-51 (config 1 of BASELINE.json): 42 scalars, Domain::Other."""
+    rng = np.random.default_rng(0xBEEF)
+    x = random_scalars(rng, 42)
+    one = pb.Hash.digest(pb.Domain.Other, x, engine)
+    h = pb.Hash(pb.Domain.Other, engine)
+    h.update(x[:3])
+    h.update(x[3:])
+    assert np.array_equal(h.finalize(), one)
+    m4 = pb.Hash.digest(pb.Domain.Merkle4, x[:4], engine)
+    assert not np.array_equal(m4, pb.Hash.digest(pb.Domain.Other, x[:4], engine))
+    want = oracle.Hash.digest(oracle.Domain.Other, [int(v) for v in unmont(x)])
+    assert [int(v) for v in unmont(one)] == want
+
+
+def test_hash_errors(engine):
+    x = mont([1, 2, 3, 4, 5])
+    with pytest.raises(pb.IOPatternViolation):
+        pb.Hash.digest(pb.Domain.Merkle4, x, engine)
+    with pytest.raises(pb.IOPatternViolation):
+        pb.Hash.digest(pb.Domain.Merkle2, x[:3], engine)
+    with pytest.raises(pb.InvalidIOPattern):
+        pb.Hash.digest(pb.Domain.Other, x[:0], engine)
+    with pytest.raises(pb.IOPatternViolation):
+        pb.Hash.digest_batch(pb.Domain.Merkle4, np.zeros((3, 5, 4), dtype=np.uint64), engine=engine)
+
+
+@pytest.mark.parametrize("in_len,out_len", [(1, 1), (2, 1), (3, 3), (4, 1), (5, 2), (4, 7), (8, 4), (9, 5),
+                                            (15, 1), (16, 8), (17, 1), (42, 1), (64, 9)])
+def test_digest_batch_vs_oracle(engine, oracle, coracle, in_len, out_len):
+    rng = np.random.default_rng(in_len * 100 + out_len)
+    n = 257
+    data = edge_and_random_scalars(rng, n * in_len).reshape(n, in_len, 4)
+    got = pb.Hash.digest_batch(pb.Domain.Other, data, out_len, engine=engine)
+    tag = _tag(oracle, [oracle.Absorb(in_len), oracle.Squeeze(out_len)], oracle.Domain.Other)
+    assert np.array_equal(got, coracle.digest(tag, data, in_len, out_len))
+
+
+def test_merkle_domains_batch(engine, oracle, coracle):
+    rng = np.random.default_rng(3)
+    for dom, od, k in ((pb.Domain.Merkle4, oracle.Domain.Merkle4, 4), (pb.Domain.Merkle2, oracle.Domain.Merkle2, 2)):
+        data = edge_and_random_scalars(rng, 1000 * k).reshape(1000, k, 4)
+        got = pb.Hash.digest_batch(dom, data, engine=engine)
+        tag = _tag(oracle, [oracle.Absorb(k), oracle.Squeeze(1)], od)
+        assert np.array_equal(got, coracle.digest(tag, data, k, 1))
+        # output_len is ignored for Merkle domains (src/hash.rs:111-115)
+        assert pb.Hash.digest_batch(dom, data[:5], 3, engine=engine).shape == (5, 1, 4)
+
+
+def test_sweep_lengths(engine, oracle, coracle):
+    """config 5 shape at reduced batch: Domain::Other, in_len 1..256 (every length up to 40, then sparse)."""
+    rng = np.random.default_rng(5)
+    for in_len in list(range(1, 41)) + [63, 64, 65, 127, 128, 200, 255, 256]:
+        n = 40
+        data = random_limbs_fast(rng, (n, in_len))
+        got = pb.Hash.digest_batch(pb.Domain.Other, data, engine=engine)
+        tag = _tag(oracle, [oracle.Absorb(in_len), oracle.Squeeze(1)], oracle.Domain.Other)
+        assert np.array_equal(got, coracle.digest(tag, data, in_len, 1)), in_len
+
+
+# ---- encryption --------------------------------------------------------------------------------------
+def test_encrypt_golden_and_errors(engine, golden):
+    for e in golden["encrypt"]:
+        msg, sec, non = mont([hx(s) for s in e["msg"]]), mont([hx(s) for s in e["secret"]]), mont(hx(e["nonce"]))
+        c = pb.encrypt(msg, sec, non, engine)
+        assert ["0x%064x" % v for v in unmont(c)] == e["cipher"]
+        assert c.shape[0] == e["L"] + 1                               # src/encryption.rs:61
+        assert np.array_equal(pb.decrypt(c, sec, non, engine), msg)
+        # tests/encryption.rs:48-115
+        wrong = sec.copy()
+        wrong[1] = mont(12345)
+        with pytest.raises(pb.DecryptionFailed):
+            pb.decrypt(c, wrong, non, engine)
+        with pytest.raises(pb.DecryptionFailed):
+            pb.decrypt(c, sec, mont(99), engine)
+        for idx in (e["L"], 0):
+            bad = mont([(int(v) + (42 if k == idx else 0)) % pb.scalar.P for k, v in enumerate(unmont(c))])
+            with pytest.raises(pb.DecryptionFailed):
+                pb.decrypt(bad, sec, non, engine)
+    # doc example src/encryption.rs:29-42
+    msg = mont([10, 20, 30])
+    c = pb.encrypt(msg, mont([5, 6]), mont(7), engine)
+    assert np.array_equal(pb.decrypt(c, mont([5, 6]), mont(7), engine), msg)
+
+
+@pytest.mark.parametrize("L", [1, 2, 3, 4, 5, 7, 8, 9, 21, 42])
+def test_encrypt_batch_vs_oracle(engine, oracle, coracle, L):
+    rng = np.random.default_rng(L)
+    n = 300
+    msg = edge_and_random_scalars(rng, n * L).reshape(n, L, 4)
+    sec = random_scalars(rng, (n, 2))
+    non = random_scalars(rng, n)
+    tag = _tag(oracle, [oracle.Absorb(2), oracle.Absorb(1), oracle.Squeeze(L), oracle.Absorb(L), oracle.Squeeze(1)],
+               oracle.Domain.Encryption)
+    c = pb.encrypt_batch(msg, sec, non, engine=engine)
+    assert np.array_equal(c, coracle.encrypt(tag, msg, L, sec, non))
+    m, ok = pb.decrypt_batch(c, sec, non, engine=engine)
+    assert ok.all() and np.array_equal(m, msg)
+    # tamper every third item in a different place
+    bad = c.copy()
+    bad[0::3, 0, 0] ^= np.uint64(1)
+    bad[1::3, L, 3] ^= np.uint64(1 << 40)
+    m2, ok2 = pb.decrypt_batch(bad, sec, non, engine=engine)
+    want_ok = np.ones(n, dtype=np.uint8)
+    want_ok[0::3] = 0
+    want_ok[1::3] = 0
+    assert np.array_equal(ok2, want_ok)
+    assert np.array_equal(m2[2::3], msg[2::3]) and not m2[0::3].any()        # failed items are zeroed
+    _, ok_o = coracle.decrypt(tag, bad, L, sec, non)
+    assert np.array_equal(ok_o, want_ok)
+
+
+# ---- Merkle tree -----------------------------------------------------------------------------------------
+def test_merkle4_tree_vs_oracle(engine, oracle, coracle):
+    rng = np.random.default_rng(8)
+    n_leaves = 4 ** 5
+    leaves = random_limbs_fast(rng, n_leaves)
+    leaves[5:9] = 0                                            # empty slots are zero (src/hash.rs:24-26)
+    nodes = pb.merkle4_build(leaves, engine)
+    tag = _tag(oracle, [oracle.Absorb(4), oracle.Squeeze(1)], oracle.Domain.Merkle4)
+    level = leaves
+    for off, m in pb.merkle.level_offsets(n_leaves):
+        want = coracle.digest(tag, level.reshape(m, 4, 4), 4, 1).reshape(m, 4)
+        assert np.array_equal(nodes[off:off + m], want)
+        level = want
+    assert nodes.shape[0] == (n_leaves - 1) // 3
+    # one level through the public helper, and the device-tensor path
+    assert np.array_equal(pb.merkle4_level(leaves, engine), nodes[:n_leaves // 4])
+    import torch
+    d = torch.from_numpy(leaves.view(np.int64)).cuda()
+    assert np.array_equal(pb.merkle4_build(d, engine).cpu().numpy().view(np.uint64), nodes)
+    with pytest.raises(pb.IOPatternViolation):
+        pb.merkle4_build(leaves[:48], engine)
+
+
+# ---- BASELINE.json full sizes: size-independent properties + multi-thread oracle --------------------------
+def test_full_size_merkle4_batch(engine, oracle, coracle):
+    """config 2: 2^20 Merkle4 digests.  (a) fast kernel == dense kernel (the reference's formulation
+    executed on the device) on 2^17 raw states; (b) the whole 2^20 batch against the multi-threaded C
+    oracle on a 2^16-item strided sample plus an XOR checksum over all items computed both ways on a
+    contiguous 2^17 prefix; (c) permuting the batch order permutes the digests (no cross-item state)."""
+    import os
+    rng = np.random.default_rng(20)
+    n = 1 << 20
+    data = random_limbs_fast(rng, (n, 4))
+    got = pb.Hash.digest_batch(pb.Domain.Merkle4, data, engine=engine)
+    tag = _tag(oracle, [oracle.Absorb(4), oracle.Squeeze(1)], oracle.Domain.Merkle4)
+    thr = max(1, min(32, os.cpu_count() or 1))
+    idx = np.arange(0, n, 16)
+    assert np.array_equal(got[idx], coracle.digest(tag, data[idx], 4, 1, threads=thr))
+    pre = 1 << 17
+    want = coracle.digest(tag, data[:pre], 4, 1, threads=thr)
+    assert np.array_equal(np.bitwise_xor.reduce(got[:pre].reshape(-1, 4), axis=0),
+                          np.bitwise_xor.reduce(want.reshape(-1, 4), axis=0))
+    perm = rng.permutation(n)
+    assert np.array_equal(pb.Hash.digest_batch(pb.Domain.Merkle4, data[perm], engine=engine), got[perm])
+    states = random_limbs_fast(rng, (pre, 5))
+    assert np.array_equal(engine.permute_batch(states), engine.permute_batch(states, dense=True))
+
+
+def test_full_size_encrypt_roundtrip(engine):
+    """config 3: 2^20 messages, L = 2 (benches/encrypt.rs:17): bit-exact round trip."""
+    rng = np.random.default_rng(21)
+    n = 1 << 20
+    msg, sec, non = random_limbs_fast(rng, (n, 2)), random_limbs_fast(rng, (n, 2)), random_limbs_fast(rng, n)
+    c = pb.encrypt_batch(msg, sec, non, engine=engine)
+    m, ok = pb.decrypt_batch(c, sec, non, engine=engine)
+    assert ok.all() and np.array_equal(m, msg)
+    non2 = non.copy()
+    non2[::2, 0] ^= np.uint64(1)
+    _, ok2 = pb.decrypt_batch(c, sec, non2, engine=engine)
+    assert not ok2[::2].any() and ok2[1::2].all()

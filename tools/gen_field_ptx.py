@@ -1,0 +1,435 @@
+"""Generator for poseidon252_b200/csrc/fr_ptx.cuh: the carry-chain primitives of the B200 Hades
+kernel as inline-PTX blocks (mad.lo.cc / madc.hi.cc pairs that ptxas fuses into IMAD.WIDE.U32[.X]).
+
+Every primitive is first built as a small IR (list of PTX ops on named 32-bit registers), which
+  * `Prog.run` EMULATES instruction by instruction (32-bit wrap, CC.CF carry flag, predicates) so
+    the sequences are verified here, without a GPU, against the integer definitions in
+    tools/hades_model.py (see tests/test_field_ptx.py), and
+  * `Prog.emit` prints as one `asm` statement per primitive (no carry flag ever crosses an asm
+    boundary).
+Ops tagged nocarry=True are the chain ends where the analysis says no carry can leave; the
+emulator asserts that.
+
+Field: BLS12-381 Fr, 8 x 32-bit limbs, p = 1 mod 2^32  =>  the Montgomery digit is m = -t0 and
+m*p0 needs no multiplier (p0 = 1): 15 IMAD.WIDE per interleaved row instead of 16.
+"""
+from __future__ import annotations
+
+import os
+import sys
+from typing import Dict, List, Sequence, Union
+
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+from hades_model import P, M32  # noqa: E402
+
+PL = [(P >> (32 * i)) & M32 for i in range(8)]
+assert PL[0] == 1 and PL[1] == M32
+
+Operand = Union[str, int]
+
+
+class Prog:
+    def __init__(self, name: str, doc: str):
+        self.name, self.doc = name, doc
+        self.ops: List[tuple] = []
+        self.ins: List[str] = []        # read-only C operands
+        self.outs: List[str] = []       # write-only C operands
+        self.inouts: List[str] = []     # read-write C operands
+        self.temps: List[str] = []
+        self.preds: List[str] = []
+
+    # -- declaration helpers
+    def inp(self, *names):
+        self.ins += names
+        return names if len(names) > 1 else names[0]
+
+    def out(self, *names):
+        self.outs += names
+        return names if len(names) > 1 else names[0]
+
+    def inout(self, *names):
+        self.inouts += names
+        return names if len(names) > 1 else names[0]
+
+    def tmp(self, *names):
+        self.temps += names
+        return names if len(names) > 1 else names[0]
+
+    def pred(self, name):
+        self.preds.append(name)
+        return name
+
+    def op(self, opc: str, d: str, *src: Operand, nocarry: bool = False, guard: str | None = None):
+        self.ops.append((opc, d, src, nocarry, guard))
+
+    # -- emulator
+    def run(self, env: Dict[str, int]) -> Dict[str, int]:
+        reg = dict(env)
+        cf = 0
+        preds: Dict[str, bool] = {}
+
+        def val(x):
+            return x & M32 if isinstance(x, int) else reg[x]
+
+        for opc, d, src, nocarry, guard in self.ops:
+            if guard is not None and not preds[guard]:
+                continue
+            base = opc.split(".")[0]
+            if base == "setp":          # setp.ge.u32 p, a, b
+                cmp = opc.split(".")[1]
+                a, b = val(src[0]), val(src[1])
+                preds[d] = {"ge": a >= b, "eq": a == b, "ne": a != b, "lt": a < b}[cmp]
+                continue
+            if base == "selp":          # selp d, a, b, p
+                reg[d] = val(src[0]) if preds[src[2]] else val(src[1])
+                continue
+            if base == "mov":
+                reg[d] = val(src[0])
+                continue
+            if base == "and":
+                reg[d] = val(src[0]) & val(src[1])
+                continue
+            uses_c = base.endswith("c") and base in ("madc", "addc", "subc")
+            sets_cc = opc.endswith(".cc.u32") or ".cc" in opc
+            cin = cf if uses_c else 0
+            if base in ("mul",):
+                prod = val(src[0]) * val(src[1])
+                full = (prod & M32) if ".lo" in opc else (prod >> 32)
+            elif base in ("mad", "madc"):
+                prod = val(src[0]) * val(src[1])
+                part = (prod & M32) if ".lo" in opc else (prod >> 32)
+                full = part + val(src[2]) + cin
+            elif base in ("add", "addc"):
+                full = val(src[0]) + val(src[1]) + cin
+            elif base in ("sub", "subc"):
+                full = val(src[0]) - val(src[1]) - cin
+                if full < 0:
+                    full += 1 << 32
+                    bout = 1
+                else:
+                    bout = 0
+                if sets_cc:
+                    cf = bout
+                else:
+                    assert not (nocarry and bout), (self.name, opc, d)
+                reg[d] = full & M32
+                continue
+            else:
+                raise ValueError(opc)
+            cout = full >> 32
+            assert cout <= 1, (self.name, opc)
+            if sets_cc:
+                cf = cout
+            else:
+                assert not (nocarry and cout), "carry lost in %s at %s %s" % (self.name, opc, d)
+            reg[d] = full & M32
+        return reg
+
+    # -- CUDA emitter
+    def emit(self) -> str:
+        order = self.outs + self.inouts + self.ins
+        idx = {n: i for i, n in enumerate(order)}
+
+        def fmt(x):
+            if isinstance(x, int):
+                return "0x%08x" % (x & M32)
+            return "%%%d" % idx[x] if x in idx else x
+
+        lines = []
+        if self.temps:
+            lines.append(".reg .u32 %s;" % ", ".join(self.temps))
+        if self.preds:
+            lines.append(".reg .pred %s;" % ", ".join(self.preds))
+        for opc, d, src, _nc, guard in self.ops:
+            g = "@%s " % guard if guard else ""
+            lines.append("%s%s %s;" % (g, opc, ", ".join([fmt(d)] + [fmt(s) for s in src])))
+        body = "\n".join('        "%s\\n\\t"' % ln for ln in ["{"] + lines + ["}"])
+        cons_out = ", ".join(['"=&r"(%s)' % n for n in self.outs] + ['"+r"(%s)' % n for n in self.inouts])
+        cons_in = ", ".join('"r"(%s)' % n for n in self.ins)
+        return "    asm(\n%s\n        : %s\n        : %s);\n" % (body, cons_out, cons_in)
+
+
+def arr(name: str, n: int) -> List[str]:
+    return ["%s[%d]" % (name, i) for i in range(n)]
+
+
+# ------------------------------------------------------------------------------------------------
+# Interleaved Montgomery product: 8 rows over an even/odd pair of 8-limb accumulators
+#   window value  W = sum ev[k] 2^(32k) + sum od[k] 2^(32(k+1))      (9 limbs)
+#   row:  W += x * y_i ;  m = -W mod 2^32 ;  W += m p ;  W >>= 32  (roles of ev/od swap)
+# Needs x + p <= 2^256 (window stays below 2^288); y is arbitrary (< 2^256).
+# ------------------------------------------------------------------------------------------------
+def _reduce_row(pg: Prog, ev, od, m):
+    pg.op("sub.u32", m, 0, ev[0])                                   # m = -W mod 2^32
+    # odd columns (1,2),(3,4),(5,6),(7,8) += m * p1,p3,p5,p7
+    pg.op("mad.lo.cc.u32", od[0], m, PL[1], od[0])
+    pg.op("madc.hi.cc.u32", od[1], m, PL[1], od[1])
+    for k in (2, 4):
+        pg.op("madc.lo.cc.u32", od[k], m, PL[k + 1], od[k])
+        pg.op("madc.hi.cc.u32", od[k + 1], m, PL[k + 1], od[k + 1])
+    pg.op("madc.lo.cc.u32", od[6], m, PL[7], od[6])
+    pg.op("madc.hi.u32", od[7], m, PL[7], od[7], nocarry=True)
+    # even columns: limb 0 + m*p0 = ev0 + m = 0 (mod 2^32), carry = (ev0 != 0); then p2,p4,p6
+    pg.op("add.cc.u32", ev[0], ev[0], m)
+    pg.op("addc.cc.u32", ev[1], ev[1], 0)
+    for k in (2, 4, 6):
+        pg.op("madc.lo.cc.u32", ev[k], m, PL[k], ev[k])
+        pg.op("madc.hi.cc.u32", ev[k + 1], m, PL[k], ev[k + 1])
+    pg.op("addc.u32", od[7], od[7], 0, nocarry=True)
+
+
+def gen_row_first() -> Prog:
+    pg = Prog("fr_row_first", "ev/od = x * yi, then one reduction row (ev[0] becomes 0)")
+    ev = pg.out(*arr("ev", 8))
+    od = pg.out(*arr("od", 8))
+    x = pg.inp(*arr("x", 8))
+    yi = pg.inp("yi")
+    m = pg.tmp("m")
+    # outputs are written before all inputs are read -> early-clobber is avoided by the C wrapper
+    for k in (0, 2, 4, 6):
+        pg.op("mul.lo.u32", ev[k], x[k], yi)
+        pg.op("mul.hi.u32", ev[k + 1], x[k], yi)
+        pg.op("mul.lo.u32", od[k], x[k + 1], yi)
+        pg.op("mul.hi.u32", od[k + 1], x[k + 1], yi)
+    _reduce_row(pg, ev, od, m)
+    return pg
+
+
+def gen_row() -> Prog:
+    pg = Prog("fr_row", "shift window by one limb (od[0] dead, od[1] orphan), += x*yi, reduce")
+    ev = pg.inout(*arr("ev", 8))
+    od = pg.inout(*arr("od", 8))
+    x = pg.inp(*arr("x", 8))
+    yi = pg.inp("yi")
+    m = pg.tmp("m")
+    pg.op("add.cc.u32", ev[0], ev[0], od[1])
+    for k in (0, 2, 4):
+        pg.op("madc.lo.cc.u32", od[k], x[k + 1], yi, od[k + 2])
+        pg.op("madc.hi.cc.u32", od[k + 1], x[k + 1], yi, od[k + 3])
+    pg.op("madc.lo.cc.u32", od[6], x[7], yi, 0)
+    pg.op("madc.hi.u32", od[7], x[7], yi, 0, nocarry=True)
+    pg.op("mad.lo.cc.u32", ev[0], x[0], yi, ev[0])
+    pg.op("madc.hi.cc.u32", ev[1], x[0], yi, ev[1])
+    for k in (2, 4, 6):
+        pg.op("madc.lo.cc.u32", ev[k], x[k], yi, ev[k])
+        pg.op("madc.hi.cc.u32", ev[k + 1], x[k], yi, ev[k + 1])
+    pg.op("addc.u32", od[7], od[7], 0, nocarry=True)
+    _reduce_row(pg, ev, od, m)
+    return pg
+
+
+def gen_merge() -> Prog:
+    pg = Prog("fr_merge", "r = (od + ev>>32): result of the last row, 8 limbs")
+    r = pg.out(*arr("r", 8))
+    ev = pg.inp(*arr("ev", 8))
+    od = pg.inp(*arr("od", 8))
+    pg.op("add.cc.u32", r[0], od[0], ev[1])
+    for k in range(1, 7):
+        pg.op("addc.cc.u32", r[k], od[k], ev[k + 1])
+    pg.op("addc.u32", r[7], od[7], 0, nocarry=True)
+    return pg
+
+
+# ------------------------------------------------------------------------------------------------
+# Mix tail: T = E + O<<32 (+ A), one Montgomery row
+# ------------------------------------------------------------------------------------------------
+def gen_mix_sum() -> Prog:
+    pg = Prog("fr_mix_sum", "t[0..8] = e[0..7] + (o[0..7] << 32)")
+    t = pg.out(*arr("t", 9))
+    e = pg.inp(*arr("e", 8))
+    o = pg.inp(*arr("o", 8))
+    pg.op("mov.u32", t[0], e[0])
+    pg.op("add.cc.u32", t[1], e[1], o[0])
+    for k in range(2, 8):
+        pg.op("addc.cc.u32", t[k], e[k], o[k - 1])
+    pg.op("addc.u32", t[8], o[7], 0, nocarry=True)
+    return pg
+
+
+def gen_redc1(with_arc: bool) -> Prog:
+    name = "fr_arc_redc1" if with_arc else "fr_redc1"
+    pg = Prog(name, "u = (t (+ a) + m p) >> 32 with m = -(t+a) mod 2^32; t is 9 limbs")
+    u = pg.out(*arr("u", 8))
+    t = pg.inout(*arr("t", 9))
+    if with_arc:
+        a = pg.inp(*arr("a", 8))
+        pg.op("add.cc.u32", t[0], t[0], a[0])
+        for k in range(1, 8):
+            pg.op("addc.cc.u32", t[k], t[k], a[k])
+        pg.op("addc.u32", t[8], t[8], 0, nocarry=True)
+    m, junk = pg.tmp("m", "junk")
+    pg.op("sub.u32", m, 0, t[0])
+    pg.op("add.cc.u32", junk, t[0], m)                       # carry = (t0 != 0)
+    for k in (0, 2, 4):
+        pg.op("madc.lo.cc.u32", u[k], m, PL[k + 1], t[k + 1])
+        pg.op("madc.hi.cc.u32", u[k + 1], m, PL[k + 1], t[k + 2])
+    pg.op("madc.lo.cc.u32", u[6], m, PL[7], t[7])
+    pg.op("madc.hi.u32", u[7], m, PL[7], t[8], nocarry=True)
+    pg.op("mad.lo.cc.u32", u[1], m, PL[2], u[1])
+    pg.op("madc.hi.cc.u32", u[2], m, PL[2], u[2])
+    for k in (3, 5):
+        pg.op("madc.lo.cc.u32", u[k], m, PL[k + 1], u[k])
+        pg.op("madc.hi.cc.u32", u[k + 1], m, PL[k + 1], u[k + 1])
+    pg.op("addc.u32", u[7], u[7], 0, nocarry=True)
+    return pg
+
+
+# ------------------------------------------------------------------------------------------------
+# Conditional subtractions / modular add / sub
+# ------------------------------------------------------------------------------------------------
+def gen_condsub255() -> Prog:
+    pg = Prog("fr_condsub255", "if (a >= 2^255) a -= p   => a < 2^255")
+    a = pg.inout(*arr("a", 8))
+    q = pg.pred("q")
+    pg.op("setp.ge.u32", q, a[7], 0x80000000)
+    pg.op("sub.cc.u32", a[0], a[0], PL[0], guard=q)
+    for k in range(1, 7):
+        pg.op("subc.cc.u32", a[k], a[k], PL[k], guard=q)
+    pg.op("subc.u32", a[7], a[7], PL[7], guard=q, nocarry=True)
+    return pg
+
+
+def gen_condsub() -> Prog:
+    pg = Prog("fr_condsub", "a < 2p  ->  a mod p in [0,p)")
+    a = pg.inout(*arr("a", 8))
+    t = pg.tmp(*["t%d" % i for i in range(8)])
+    brw = pg.tmp("brw")
+    q = pg.pred("q")
+    pg.op("sub.cc.u32", t[0], a[0], PL[0])
+    for k in range(1, 8):
+        pg.op("subc.cc.u32", t[k], a[k], PL[k])
+    pg.op("subc.u32", brw, 0, 0)                   # 0xffffffff if a < p
+    pg.op("setp.eq.u32", q, brw, 0)
+    for k in range(8):
+        pg.op("selp.u32", a[k], t[k], a[k], q)
+    return pg
+
+
+def gen_add() -> Prog:
+    pg = Prog("fr_add_lazy", "r = a + b (no reduction; caller guarantees a + b < 2^256)")
+    r = pg.out(*arr("r", 8))
+    a = pg.inp(*arr("a", 8))
+    b = pg.inp(*arr("b", 8))
+    pg.op("add.cc.u32", r[0], a[0], b[0])
+    for k in range(1, 7):
+        pg.op("addc.cc.u32", r[k], a[k], b[k])
+    pg.op("addc.u32", r[7], a[7], b[7], nocarry=True)
+    return pg
+
+
+def gen_submod() -> Prog:
+    pg = Prog("fr_sub_mod", "r = a - b mod p for a, b in [0,p)  (BlsScalar -)")
+    r = pg.out(*arr("r", 8))
+    a = pg.inp(*arr("a", 8))
+    b = pg.inp(*arr("b", 8))
+    brw = pg.tmp("brw")
+    msk = pg.tmp(*["k%d" % i for i in range(8)])
+    pg.op("sub.cc.u32", r[0], a[0], b[0])
+    for k in range(1, 8):
+        pg.op("subc.cc.u32", r[k], a[k], b[k])
+    pg.op("subc.u32", brw, 0, 0)                   # all-ones if a < b
+    for k in range(8):
+        pg.op("and.b32", msk[k], brw, PL[k])
+    pg.op("add.cc.u32", r[0], r[0], msk[0])
+    for k in range(1, 7):
+        pg.op("addc.cc.u32", r[k], r[k], msk[k])
+    pg.op("addc.u32", r[7], r[7], msk[7])
+    return pg
+
+
+ALL = [gen_row_first(), gen_row(), gen_merge(), gen_mix_sum(), gen_redc1(True), gen_redc1(False),
+       gen_condsub255(), gen_condsub(), gen_add(), gen_submod()]
+BY_NAME = {p.name: p for p in ALL}
+
+SIGS = {
+    "fr_row_first": "uint32_t (&ev)[8], uint32_t (&od)[8], const uint32_t (&x)[8], uint32_t yi",
+    "fr_row": "uint32_t (&ev)[8], uint32_t (&od)[8], const uint32_t (&x)[8], uint32_t yi",
+    "fr_merge": "uint32_t (&r)[8], const uint32_t (&ev)[8], const uint32_t (&od)[8]",
+    "fr_mix_sum": "uint32_t (&t)[9], const uint32_t (&e)[8], const uint32_t (&o)[8]",
+    "fr_arc_redc1": "uint32_t (&u)[8], uint32_t (&t)[9], const uint32_t (&a)[8]",
+    "fr_redc1": "uint32_t (&u)[8], uint32_t (&t)[9]",
+    "fr_condsub255": "uint32_t (&a)[8]",
+    "fr_condsub": "uint32_t (&a)[8]",
+    "fr_add_lazy": "uint32_t (&r)[8], const uint32_t (&a)[8], const uint32_t (&b)[8]",
+    "fr_sub_mod": "uint32_t (&r)[8], const uint32_t (&a)[8], const uint32_t (&b)[8]",
+}
+
+
+# ---- emulator-level compositions (mirror the C++ wrappers in fr_ptx.cuh) -----------------------
+def _get(reg, name, n):
+    return [reg["%s[%d]" % (name, i)] for i in range(n)]
+
+
+def _put(name, vals):
+    return {"%s[%d]" % (name, i): v for i, v in enumerate(vals)}
+
+
+def emu_montmul(x: int, y: int) -> int:
+    xl = [(x >> (32 * i)) & M32 for i in range(8)]
+    yl = [(y >> (32 * i)) & M32 for i in range(8)]
+    env = {**_put("x", xl), "yi": yl[0]}
+    reg = BY_NAME["fr_row_first"].run(env)
+    A, B = _get(reg, "ev", 8), _get(reg, "od", 8)
+    for i in range(1, 8):
+        # roles swap each row: previous od becomes ev
+        env = {**_put("x", xl), "yi": yl[i], **_put("ev", B), **_put("od", A)}
+        reg = BY_NAME["fr_row"].run(env)
+        A, B = _get(reg, "ev", 8), _get(reg, "od", 8)
+    reg = BY_NAME["fr_merge"].run({**_put("ev", A), **_put("od", B)})
+    return sum(v << (32 * i) for i, v in enumerate(_get(reg, "r", 8)))
+
+
+def emu_mix_lane(e_cols: Sequence[int], o_cols: Sequence[int], arc: int | None) -> int:
+    """e_cols/o_cols: the four 64-bit column sums of the even / odd limbs."""
+    e = [(c >> (32 * h)) & M32 for c in e_cols for h in (0, 1)]
+    o = [(c >> (32 * h)) & M32 for c in o_cols for h in (0, 1)]
+    reg = BY_NAME["fr_mix_sum"].run({**_put("e", e), **_put("o", o)})
+    t = _get(reg, "t", 9)
+    if arc is None:
+        reg = BY_NAME["fr_redc1"].run(_put("t", t))
+    else:
+        reg = BY_NAME["fr_arc_redc1"].run({**_put("t", t), **_put("a", [(arc >> (32 * i)) & M32 for i in range(8)])})
+    return sum(v << (32 * i) for i, v in enumerate(_get(reg, "u", 8)))
+
+
+def emu_unary(name: str, a: int) -> int:
+    reg = BY_NAME[name].run(_put("a", [(a >> (32 * i)) & M32 for i in range(8)]))
+    return sum(v << (32 * i) for i, v in enumerate(_get(reg, "a", 8)))
+
+
+def emu_binary(name: str, a: int, b: int) -> int:
+    reg = BY_NAME[name].run({**_put("a", [(a >> (32 * i)) & M32 for i in range(8)]),
+                             **_put("b", [(b >> (32 * i)) & M32 for i in range(8)])})
+    return sum(v << (32 * i) for i, v in enumerate(_get(reg, "r", 8)))
+
+
+HEADER = '''// GENERATED by tools/gen_field_ptx.py -- do not edit by hand.
+// Carry-chain primitives for BLS12-381 Fr on 8 x 32-bit limbs (sm_100a).  Each primitive is ONE asm
+// statement (the carry flag never crosses a statement); mad.lo.cc/madc.hi.cc pairs become
+// IMAD.WIDE.U32[.X] in SASS.  Verified instruction-by-instruction by the emulator in the generator
+// (tests/test_field_ptx.py) against the integer definitions of tools/hades_model.py.
+#pragma once
+#include <stdint.h>
+
+namespace p252 {
+
+'''
+
+
+def emit_header() -> str:
+    s = HEADER
+    for pg in ALL:
+        s += "// %s\n" % pg.doc
+        s += "__device__ __forceinline__ void %s(%s) {\n" % (pg.name, SIGS[pg.name])
+        s += pg.emit()
+        s += "}\n\n"
+    s += "}  // namespace p252\n"
+    return s
+
+
+if __name__ == "__main__":
+    out = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "poseidon252_b200", "csrc",
+                       "fr_ptx.cuh")
+    with open(out, "w") as f:
+        f.write(emit_header())
+    print("wrote", os.path.normpath(out))
