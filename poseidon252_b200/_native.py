@@ -57,7 +57,7 @@ def lib():
                 "poseidon252_b200: %s is missing. Build the sm_100a library first "
                 "(`python -m poseidon252_b200.build` or __graft_entry__.build()). "
                 "There is no CPU fallback for the batch path." % LIB_PATH)
-        handle = ctypes.CDLL(LIB_PATH, mode=ctypes.RTLD_GLOBAL)
+        handle = ctypes.CDLL(LIB_PATH)
         for name, (res, args) in SIGNATURES.items():
             fn = getattr(handle, name)       # AttributeError = header/library mismatch: fail loudly
             fn.restype = res

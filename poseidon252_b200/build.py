@@ -47,7 +47,7 @@ def build(force=False, verbose=False):
         return LIB
     generate()
     os.makedirs(os.path.dirname(LIB), exist_ok=True)
-    cmd = [nvcc()] + NVCC_FLAGS + ["-o", LIB] + SOURCES + ["-lnccl"]
+    cmd = [nvcc()] + NVCC_FLAGS + ["-o", LIB] + SOURCES + ["-ldl"]
     res = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     log = os.path.join(PKG, "lib", "build.log")
     with open(log, "w") as f:

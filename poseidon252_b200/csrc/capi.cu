@@ -8,7 +8,8 @@
 //   Error                           src/error.rs:11-44      -> p252_status
 // No permutation is ever computed on the host: without a CUDA device every batch call fails.
 #include <cuda_runtime.h>
-#include <nccl.h>
+#include <dlfcn.h>
+#include <nccl.h>   // types only: the NCCL entry points are resolved at run time (see NcclApi below)
 
 #include <algorithm>
 #include <cstdio>
@@ -52,6 +53,41 @@ struct p252_ctx {
 
 namespace {
 
+// NCCL is bound lazily with dlopen so that (a) single-GPU users carry no NCCL dependency and (b) inside a
+// process that already loaded a libnccl.so.2 (e.g. the one bundled with PyTorch) that same copy is used
+// instead of a second, possibly older, system copy.
+struct NcclApi {
+    void* handle = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+    const char* (*GetErrorString)(ncclResult_t) = nullptr;
+    bool ok = false;
+};
+
+NcclApi& nccl() {
+    static NcclApi api;
+    if (api.handle) return api;
+    const char* names[] = {"libnccl.so.2", "libnccl.so"};
+    for (const char* n : names) {
+        api.handle = dlopen(n, RTLD_NOW | RTLD_NOLOAD);     // a copy this process already has
+        if (api.handle) break;
+    }
+    for (const char* n : names) {
+        if (api.handle) break;
+        api.handle = dlopen(n, RTLD_NOW | RTLD_LOCAL);
+    }
+    if (!api.handle) return api;
+    api.GetUniqueId = reinterpret_cast<decltype(api.GetUniqueId)>(dlsym(api.handle, "ncclGetUniqueId"));
+    api.CommInitRank = reinterpret_cast<decltype(api.CommInitRank)>(dlsym(api.handle, "ncclCommInitRank"));
+    api.CommDestroy = reinterpret_cast<decltype(api.CommDestroy)>(dlsym(api.handle, "ncclCommDestroy"));
+    api.AllGather = reinterpret_cast<decltype(api.AllGather)>(dlsym(api.handle, "ncclAllGather"));
+    api.GetErrorString = reinterpret_cast<decltype(api.GetErrorString)>(dlsym(api.handle, "ncclGetErrorString"));
+    api.ok = api.GetUniqueId && api.CommInitRank && api.CommDestroy && api.AllGather && api.GetErrorString;
+    return api;
+}
+
 struct DeviceGuard {
     int prev = -1;
     explicit DeviceGuard(int dev) {
@@ -71,7 +107,7 @@ int fail_cuda(p252_ctx* ctx, cudaError_t e, const char* where) {
     return e == cudaErrorMemoryAllocation ? P252_ERR_OUT_OF_MEMORY : P252_ERR_CUDA;
 }
 int fail_nccl(p252_ctx* ctx, ncclResult_t e, const char* where) {
-    if (ctx) ctx->last_error = std::string(where) + ": " + ncclGetErrorString(e);
+    if (ctx) ctx->last_error = std::string(where) + ": " + (nccl().ok ? nccl().GetErrorString(e) : "NCCL unavailable");
     return P252_ERR_NCCL;
 }
 #define CU(call)                                              \
@@ -252,7 +288,7 @@ int p252_create(int device, p252_ctx** out) { return p252_create_on_stream(devic
 void p252_destroy(p252_ctx* ctx) {
     if (!ctx) return;
     DeviceGuard g(ctx->device);
-    if (ctx->comm) ncclCommDestroy(ctx->comm);
+    if (ctx->comm && nccl().ok) nccl().CommDestroy(ctx->comm);
     if (ctx->comm_stream) cudaStreamDestroy(ctx->comm_stream);
     for (int s = 0; s < kSlots; ++s) {
         if (ctx->slots[s].stream) {
@@ -554,8 +590,9 @@ int p252_dist_unique_id(uint8_t id[P252_NCCL_UNIQUE_ID_BYTES]) {
     static_assert(sizeof(ncclUniqueId) <= P252_NCCL_UNIQUE_ID_BYTES, "unique id size");
     p252_ctx* ctx = nullptr;
     if (!id) return P252_ERR_INVALID_ARGUMENT;
+    if (!nccl().ok) return fail_nccl(ctx, ncclSystemError, "dlopen(libnccl.so.2)");
     ncclUniqueId u;
-    NC(ncclGetUniqueId(&u));
+    NC(nccl().GetUniqueId(&u));
     memset(id, 0, P252_NCCL_UNIQUE_ID_BYTES);
     memcpy(id, &u, sizeof u);
     return P252_OK;
@@ -565,9 +602,10 @@ int p252_dist_init(p252_ctx* ctx, const uint8_t id[P252_NCCL_UNIQUE_ID_BYTES], i
     if (!ctx || !id || nranks < 1 || rank < 0 || rank >= nranks) return P252_ERR_INVALID_ARGUMENT;
     if (ctx->comm) return P252_ERR_INVALID_ARGUMENT;
     DeviceGuard g(ctx->device);
+    if (!nccl().ok) return fail_nccl(ctx, ncclSystemError, "dlopen(libnccl.so.2)");
     ncclUniqueId u;
     memcpy(&u, id, sizeof u);
-    NC(ncclCommInitRank(&ctx->comm, nranks, u, rank));
+    NC(nccl().CommInitRank(&ctx->comm, nranks, u, rank));
     ctx->rank = rank;
     ctx->nranks = nranks;
     CU(cudaStreamCreateWithFlags(&ctx->comm_stream, cudaStreamNonBlocking));
@@ -579,7 +617,7 @@ int p252_dist_finalize(p252_ctx* ctx) {
     DeviceGuard g(ctx->device);
     if (ctx->comm) {
         CU(cudaStreamSynchronize(ctx->comm_stream));
-        NC(ncclCommDestroy(ctx->comm));
+        NC(nccl().CommDestroy(ctx->comm));
         ctx->comm = nullptr;
     }
     if (ctx->comm_stream) {
@@ -625,7 +663,7 @@ int p252_merkle4_build_dist(p252_ctx* ctx, const p252_fr* leaves_shard, size_t n
             if (G > 1) {
                 CU(cudaEventRecord(ctx->ev_level, ctx->stream));
                 CU(cudaStreamWaitEvent(ctx->comm_stream, ctx->ev_level, 0));
-                NC(ncclAllGather(level + (size_t)r * cnt, level, cnt * 4, ncclUint64, ctx->comm, ctx->comm_stream));
+                NC(nccl().AllGather(level + (size_t)r * cnt, level, cnt * 4, ncclUint64, ctx->comm, ctx->comm_stream));
                 CU(cudaEventRecord(ctx->ev_comm, ctx->comm_stream));
                 gathered_below = false;   // in flight
             }
