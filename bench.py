@@ -43,38 +43,61 @@ def env_int(name, default):
         return default
 
 
-class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons streamed (-lms) DURING the timed region (B200_PROFILING.md)."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
-        super().__init__(daemon=True)
-        self.index, self.rows, self._stop = index, [], threading.Event()
+        self.index, self.proc = index, None
 
-    def run(self):
-        while not self._stop.is_set():
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            time.sleep(0.15)                      # let the first samples arrive before the timed region
+        except Exception:
+            self.proc = None
+
+    def stop(self, t_begin=None, t_end=None):
+        rows = []
+        if self.proc is not None:
+            time.sleep(0.05)
+            self.proc.terminate()
             try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
-                parts = [p.strip() for p in out.strip().split(",")]
-                if len(parts) >= 7:
-                    self.rows.append(parts)
+                out, _ = self.proc.communicate(timeout=5)
             except Exception:
-                pass
-            self._stop.wait(0.1)
-
-    def stop(self):
-        self._stop.set()
-        self.join(timeout=6)
-        if not self.rows:
+                self.proc.kill()
+                out = ""
+            for ln in out.splitlines():
+                parts = [p.strip() for p in ln.split(",")]
+                if len(parts) >= 7:
+                    try:
+                        float(parts[0])
+                        rows.append(parts)
+                    except ValueError:
+                        pass
+        if not rows:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
-        sm = [float(r[0]) for r in self.rows]
+        sm = [float(r[0]) for r in rows]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [n for k, n in enumerate(names) if any(r[3 + k].lower().startswith("active") for r in self.rows)]
-        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": float(self.rows[0][1]), "reasons": reasons,
-                "power_w_max": max(float(r[2]) for r in self.rows), "samples": len(self.rows)}
+        reasons = [n for k, n in enumerate(names) if any(r[3 + k].lower().startswith("active") for r in rows)]
+        return {"sm_mhz": statistics.median(sm), "sm_min_mhz": min(sm), "sm_max_mhz": float(rows[0][1]),
+                "reasons": reasons, "power_w_max": max(float(r[2]) for r in rows), "samples": len(rows)}
+
+
+def usable_cores():
+    """Host threads this process may really use: affinity mask capped by the cgroup CPU quota."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    try:
+        quota, period = open("/sys/fs/cgroup/cpu.max").read().split()
+        if quota != "max":
+            n = max(1, min(n, int(float(quota) / float(period) + 0.5)))
+    except Exception:
+        pass
+    return n
 
 
 def measured_peaks():
@@ -116,7 +139,7 @@ def cpu_rate(n_items, threads, in_len=4):
 
 
 def cpu_baseline_block(target_seconds=10.0):
-    threads = os.cpu_count() or 1
+    threads = usable_cores()
     probe_n = 4096 * threads
     cpu_rate(probe_n, threads)
     rate, _ = cpu_rate(probe_n, threads)
@@ -130,7 +153,7 @@ def cpu_baseline_block(target_seconds=10.0):
 def run_reference_arm(args, rank, world):
     if rank != 0:
         return
-    threads = os.cpu_count() or 1
+    threads = usable_cores()
     probe_n = 4096 * threads
     cpu_rate(probe_n, threads)
     rate, _ = cpu_rate(probe_n, threads)
@@ -159,7 +182,7 @@ def run_reference_arm(args, rank, world):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=40)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="merkle4", choices=["merkle4", "encrypt", "permute", "sweep", "tree"])

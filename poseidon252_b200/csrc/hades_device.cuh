@@ -48,14 +48,20 @@ __device__ __forceinline__ void montmul(uint32_t (&r)[8], const uint32_t (&x)[8]
     fr_merge(r, b, a);
 }
 
+// r = (a*a + m p) / 2^256: 36-product square, then eight Montgomery rows on the low half + high half.
+__device__ __forceinline__ void montsqr(uint32_t (&r)[8], const uint32_t (&a)[8]) {
+    uint32_t t[16];
+    fr_sqr_wide(t, a);
+    fr_redc_wide(r, t);
+}
+
 // z = u^5 / R^4 (unreduced): two squarings and one product like quintic_s_box
-// (/root/reference/src/hades/permutation/scalar.rs:50-52).  u < 1.0003 p  =>  z < 1.71 p.
+// (/root/reference/src/hades/permutation/scalar.rs:50-52).  u < 1.0003 p  =>  z < 1.89 p.
 __device__ __forceinline__ void sbox(uint32_t (&z)[8], const uint32_t (&u)[8]) {
     uint32_t a[8], b[8];
-    montmul(a, u, u);
-    fr_condsub255(a);          // a < 2^255 so that a + p <= 2^256 (row-operand bound)
-    montmul(b, a, a);
-    montmul(z, u, b);
+    montsqr(a, u);             // < 1.4533 p
+    montsqr(b, a);             // < 1.9564 p
+    montmul(z, u, b);          // row operand u (u + p <= 2^256), result < 1.8861 p
 }
 
 __device__ __forceinline__ void load_const(uint32_t (&d)[8], const uint32_t* c) {

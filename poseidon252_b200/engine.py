@@ -34,6 +34,15 @@ class Engine:
             self._ctx = ctypes.c_void_p()
             raise EngineError(rc, self._lib.p252_strerror(rc).decode())
         self._dist = False
+        self._stream_handle = None if stream is None else int(stream)
+
+    def _fence_torch(self):
+        """Device tensors are produced on torch's current stream; unless the engine was bound to that
+        very stream, wait for it before enqueueing on ours (cross-stream ordering)."""
+        import torch
+        cur = torch.cuda.current_stream(self.device)
+        if self._stream_handle is None or int(cur.cuda_stream) != self._stream_handle:
+            cur.synchronize()
 
     # -- lifetime ---------------------------------------------------------------------------------
     def close(self):
@@ -73,6 +82,7 @@ class Engine:
                 raise EngineError(-1, "device buffers must be contiguous 64-bit integer tensors")
             if tuple(x.shape[-len(shape_tail):]) != tuple(shape_tail):
                 raise EngineError(-1, "expected trailing shape %s, got %s" % (shape_tail, tuple(x.shape)))
+            self._fence_torch()
             return x.data_ptr(), tuple(x.shape[:-len(shape_tail)]), _native.MEM_DEVICE, x
         a = np.ascontiguousarray(x, dtype=np.uint64)
         if tuple(a.shape[-len(shape_tail):]) != tuple(shape_tail):
@@ -98,6 +108,7 @@ class Engine:
             res = keep.clone() if out is None else out
             if out is not None and out is not keep:
                 out.copy_(keep)
+            self._fence_torch()
         else:
             res = keep.copy() if (out is None and keep is states) else keep
         fn = self._lib.p252_permute_batch_dense if dense else self._lib.p252_permute_batch

@@ -38,6 +38,24 @@ def test_montmul_rows():
         assert g.emu_montmul(x, y) == mm(x, y)
 
 
+def test_montsqr_and_wide_reduction():
+    rnd = random.Random(4)
+    P, T = hm.P, hm.TWO256
+    for a in [0, 1, P - 1, P, (1 << 255) - 1, 1 << 255, T - P, hm.M32, T - 1]:
+        if mm(a, a) < T:
+            assert g.emu_montsqr(a) == mm(a, a)
+    for _ in range(400):
+        a = rnd.randrange(int(1.6 * P))
+        if rnd.random() < 0.3:
+            a = int(1.6 * P) - rnd.randrange(1 << rnd.randrange(1, 250))
+        if rnd.random() < 0.1:
+            a = rnd.randrange(1 << rnd.randrange(1, 256))
+        assert g.emu_montsqr(a) == mm(a, a)
+        x, y = rnd.randrange(int(2.2 * P)), rnd.randrange(int(1.2 * P))
+        if mm(x, y) < T:
+            assert g.emu_redc_wide(x * y) == mm(x, y)
+
+
 def test_mix_tail():
     rnd = random.Random(2)
     for _ in range(500):
@@ -76,7 +94,8 @@ def test_scaled_lazy_model_equals_oracle(oracle):
         got = hm.permute_model([x * hm.R % hm.P for x in c])
         assert got == [x * hm.R % hm.P for x in oracle.perm(c)]
     # operand bounds the CUDA code relies on (DESIGN.md "Operand bounds")
-    assert hm.Bounds.seen["sqr1"] < 1.4534 and hm.Bounds.seen["x5"] < 1.71 and hm.Bounds.seen["gmul"] < 1.78
+    assert hm.Bounds.seen["sqr1"] < 1.4534 and hm.Bounds.seen["sqr2"] < 1.9565
+    assert hm.Bounds.seen["x5"] < 1.8862 and hm.Bounds.seen["gmul"] < 1.855
 
 
 def test_model_constants_equal_oracle(oracle):

@@ -89,6 +89,10 @@ class Prog:
             if base == "and":
                 reg[d] = val(src[0]) & val(src[1])
                 continue
+            if base == "shf":           # shf.l.wrap.b32 d, lo, hi, n : upper word of (hi:lo) << n
+                n = val(src[2]) & 31
+                reg[d] = (((val(src[1]) << 32) | val(src[0])) << n >> 32) & M32
+                continue
             uses_c = base.endswith("c") and base in ("madc", "addc", "subc")
             sets_cc = opc.endswith(".cc.u32") or ".cc" in opc
             cin = cf if uses_c else 0
@@ -337,8 +341,159 @@ def gen_submod() -> Prog:
     return pg
 
 
+
+# ------------------------------------------------------------------------------------------------
+# Chain builder with "fresh" (not yet written, logically zero) accumulator limbs
+# ------------------------------------------------------------------------------------------------
+class Acc:
+    """Accumulator limbs by absolute index; a limb is 'fresh' until first written."""
+
+    def __init__(self, pg: Prog, prefix: str, n: int, preset: Dict[int, str] | None = None):
+        self.pg, self.n = pg, n
+        self.name = {k: "%s%d" % (prefix, k) for k in range(n)}
+        self.defined = set()
+        if preset:
+            for k, nm in preset.items():
+                self.name[k] = nm
+                self.defined.add(k)
+        self.temps = [self.name[k] for k in range(n) if not (preset and k in preset)]
+
+    def src(self, k) -> Operand:
+        return self.name[k] if k in self.defined else 0
+
+
+def chain_products(pg: Prog, acc: Acc, prods: Sequence[tuple], cf_live: bool = False, capture: bool = True) -> None:
+    """prods: [(a, b, pos)] with consecutive 64-bit columns pos, pos+2, ...: acc[pos,pos+1] += a*b, carry
+    running through the columns; the final carry is captured into acc[last+2] (asserted not to overflow)."""
+    for (a, b, pos) in prods:
+        for half, k in (("lo", pos), ("hi", pos + 1)):
+            d = acc.name[k]
+            if k in acc.defined or cf_live:
+                opc = ("madc.%s.cc.u32" if cf_live else "mad.%s.cc.u32") % half
+                pg.op(opc, d, a, b, acc.src(k))
+                cf_live = True
+            else:
+                pg.op("mul.%s.u32" % half, d, a, b)
+            acc.defined.add(k)
+    if cf_live and capture:
+        k = prods[-1][2] + 2
+        pg.op("addc.u32", acc.name[k], acc.src(k), 0, nocarry=True)
+        acc.defined.add(k)
+
+
+def gen_sqr_product() -> Prog:
+    """t[0..15] = a^2: 28 off-diagonal products once (even/odd columns), doubled by a funnel shift that is
+    folded into the carry chain of the 8 diagonal squares  =>  36 IMAD.WIDE instead of 64."""
+    pg = Prog("fr_sqr_wide", "t[0..15] = a * a (full 512-bit square)")
+    t = pg.out(*arr("t", 16))
+    a = pg.inp(*arr("a", 8))
+    E, O = Acc(pg, "e", 17), Acc(pg, "o", 17)
+    pg.tmp(*E.temps)
+    pg.tmp(*O.temps)
+    for i in range(7):
+        odd = [(a[i], a[j], i + j) for j in range(i + 1, 8, 2)]
+        even = [(a[i], a[j], i + j) for j in range(i + 2, 8, 2)]
+        if odd:
+            chain_products(pg, O, odd)
+        if even:
+            chain_products(pg, E, even)
+    # S = E + O  (limb 0 is empty: the lowest off-diagonal product sits at limb 1)
+    S = ["s%d" % k for k in range(16)]
+    pg.tmp(*S)
+    first = True
+    for k in range(1, 16):
+        if k not in E.defined and k not in O.defined and first:
+            pg.op("mov.u32", S[k], 0)
+            continue
+        pg.op("add.cc.u32" if first else "addc.cc.u32", S[k], E.src(k), O.src(k))
+        first = False
+    assert 16 not in E.defined and 16 not in O.defined
+    # t = 2 S + sum a_i^2 2^(64 i): x_k = (S_k << 1) | (S_{k-1} >> 31), folded into the diagonal chain
+    X = ["x%d" % k for k in range(16)]
+    pg.tmp(*X)
+    pg.op("shf.l.wrap.b32", X[1], 0, S[1], 1)
+    for k in range(2, 16):
+        pg.op("shf.l.wrap.b32", X[k], S[k - 1], S[k], 1)
+    pg.op("mul.lo.u32", t[0], a[0], a[0])
+    pg.op("mad.hi.cc.u32", t[1], a[0], a[0], X[1])
+    for i in range(1, 8):
+        pg.op("madc.lo.cc.u32", t[2 * i], a[i], a[i], X[2 * i])
+        if i < 7:
+            pg.op("madc.hi.cc.u32", t[2 * i + 1], a[i], a[i], X[2 * i + 1])
+        else:
+            pg.op("madc.hi.u32", t[15], a[7], a[7], X[15], nocarry=True)
+    return pg
+
+
+def gen_redc_wide() -> Prog:
+    """r = (t_lo + M p) / 2^256 + t_hi with M = -t_lo / p mod 2^256: eight Montgomery rows on the low half
+    (9-limb even/odd window, pure register renaming between rows), then one 8-limb addition."""
+    pg = Prog("fr_redc_wide", "r = redc(t[0..7]) + t[8..15]  (t is a 512-bit product)")
+    r = pg.out(*arr("r", 8))
+    t = pg.inp(*arr("t", 16))
+    uid = [0]
+
+    def fresh(prefix):
+        uid[0] += 1
+        nm = "%s%d" % (prefix, uid[0])
+        pg.tmp(nm)
+        return nm
+
+    # window limbs as register names or None (= zero / not yet written)
+    EV: List = [fresh("w") for _ in range(8)]
+    for k in range(8):
+        pg.op("mov.u32", EV[k], t[k])
+    OD: List = [None] * 8
+    orphan = None
+    for row in range(8):
+        cf = False
+        if orphan is not None:
+            pg.op("add.cc.u32", EV[0], EV[0], orphan)
+            cf = True
+        m = fresh("m")
+        pg.op("sub.u32", m, 0, EV[0])
+        # odd columns += m * (p1, p3, p5, p7)
+        for idx, k in enumerate((0, 2, 4, 6)):
+            pj = PL[k + 1]
+            for half, kk in (("lo", k), ("hi", k + 1)):
+                last = (kk == 7)
+                if OD[kk] is not None or cf:
+                    src = OD[kk] if OD[kk] is not None else 0
+                    if OD[kk] is None:
+                        OD[kk] = fresh("w")
+                    opc = ("madc.%s" if cf else "mad.%s") % half + (".u32" if last else ".cc.u32")
+                    pg.op(opc, OD[kk], m, pj, src, nocarry=last)
+                    cf = not last
+                else:
+                    OD[kk] = fresh("w")
+                    pg.op("mul.%s.u32" % half, OD[kk], m, pj)
+        # even columns: limb 0 cancels (carry = EV0 != 0), then p2, p4, p6; carry out joins limb 8
+        junk = fresh("j")
+        pg.op("add.cc.u32", junk, EV[0], m)
+        pg.op("addc.cc.u32", EV[1], EV[1], 0)
+        for k in (2, 4, 6):
+            pg.op("madc.lo.cc.u32", EV[k], m, PL[k], EV[k])
+            pg.op("madc.hi.cc.u32", EV[k + 1], m, PL[k], EV[k + 1])
+        pg.op("addc.u32", OD[7], OD[7], 0, nocarry=True)
+        # shift the window down one limb: pure renaming
+        orphan = EV[1]
+        EV, OD = OD, [EV[2], EV[3], EV[4], EV[5], EV[6], EV[7], None, None]
+    # merge window + orphan, then add the high half of t
+    s = [fresh("q") for _ in range(8)]
+    pg.op("add.cc.u32", s[0], EV[0], orphan)
+    for k in range(1, 7):
+        pg.op("addc.cc.u32", s[k], EV[k], OD[k - 1])
+    pg.op("addc.u32", s[7], EV[7], 0, nocarry=True)
+    pg.op("add.cc.u32", r[0], s[0], t[8])
+    for k in range(1, 7):
+        pg.op("addc.cc.u32", r[k], s[k], t[8 + k])
+    pg.op("addc.u32", r[7], s[7], t[15], nocarry=True)
+    return pg
+
+
 ALL = [gen_row_first(), gen_row(), gen_merge(), gen_mix_sum(), gen_redc1(True), gen_redc1(False),
-       gen_condsub255(), gen_condsub(), gen_add(), gen_submod()]
+       gen_condsub255(), gen_condsub(), gen_add(), gen_submod(),
+       gen_sqr_product(), gen_redc_wide()]
 BY_NAME = {p.name: p for p in ALL}
 
 SIGS = {
@@ -352,6 +507,8 @@ SIGS = {
     "fr_condsub": "uint32_t (&a)[8]",
     "fr_add_lazy": "uint32_t (&r)[8], const uint32_t (&a)[8], const uint32_t (&b)[8]",
     "fr_sub_mod": "uint32_t (&r)[8], const uint32_t (&a)[8], const uint32_t (&b)[8]",
+    "fr_sqr_wide": "uint32_t (&t)[16], const uint32_t (&a)[8]",
+    "fr_redc_wide": "uint32_t (&r)[8], const uint32_t (&t)[16]",
 }
 
 
@@ -376,6 +533,19 @@ def emu_montmul(x: int, y: int) -> int:
         reg = BY_NAME["fr_row"].run(env)
         A, B = _get(reg, "ev", 8), _get(reg, "od", 8)
     reg = BY_NAME["fr_merge"].run({**_put("ev", A), **_put("od", B)})
+    return sum(v << (32 * i) for i, v in enumerate(_get(reg, "r", 8)))
+
+
+def emu_montsqr(a: int) -> int:
+    reg = BY_NAME["fr_sqr_wide"].run(_put("a", [(a >> (32 * i)) & M32 for i in range(8)]))
+    t = _get(reg, "t", 16)
+    assert sum(v << (32 * i) for i, v in enumerate(t)) == a * a, "square product wrong"
+    reg = BY_NAME["fr_redc_wide"].run(_put("t", t))
+    return sum(v << (32 * i) for i, v in enumerate(_get(reg, "r", 8)))
+
+
+def emu_redc_wide(t: int) -> int:
+    reg = BY_NAME["fr_redc_wide"].run(_put("t", [(t >> (32 * i)) & M32 for i in range(16)]))
     return sum(v << (32 * i) for i, v in enumerate(_get(reg, "r", 8)))
 
 

@@ -13,7 +13,7 @@ The kernel keeps every lane as an integer `stored` with  true = kappa_r * stored
 round-dependent, data-independent scale kappa_r:
 
   * montmul(a,b) = (a*b + m*p)/2^256 (m = -a*b/p mod 2^256)  -- unreduced Montgomery product
-  * full round   : z = montmul(montsqr(montsqr(u)), u)            (scale kappa^5 R^4)
+  * full round   : z = montmul(u, montsqr(montsqr(u)))            (scale kappa^5 R^4)
   * partial round: lane 4 gets one extra montmul by G_r = kappa_r^4 R^5 so that its scale equals
                    the scale kappa_r of the four linear lanes
   * mix          : T_i = A_{r+1,i} + sum_j c_ij z_j  (plain small-integer MADs, 9 limbs), then one
@@ -154,9 +154,21 @@ def condsub(a: int) -> int:
     return a
 
 
+def montsqr(a: int, site: str = "montsqr") -> int:
+    """(a*a + m*p) / 2^256: product first (36 limb products), then eight Montgomery rows on the low half
+    plus the high half.  No row-operand constraint; only the result must fit 8 limbs."""
+    assert 0 <= a < TWO256
+    t = a * a
+    m = (-t * pow(P, -1, TWO256)) % TWO256
+    r = (t + m * P) >> 256
+    assert r < TWO256, "montsqr result overflows 8 limbs"
+    Bounds.note(site, r)
+    return r
+
+
 def sbox(u: int) -> int:
-    a = condsub255(montmul(u, u, "sqr1"))
-    b = montmul(a, a, "sqr2")
+    a = montsqr(u, "sqr1")
+    b = montsqr(a, "sqr2")
     return montmul(u, b, "x5")
 
 
