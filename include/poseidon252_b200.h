@@ -148,6 +148,19 @@ int p252_merkle4_build(p252_ctx* ctx, const p252_fr* leaves, size_t n_leaves, p2
 int p252_dist_unique_id(uint8_t id[P252_NCCL_UNIQUE_ID_BYTES]);
 int p252_dist_init(p252_ctx* ctx, const uint8_t id[P252_NCCL_UNIQUE_ID_BYTES], int rank, int nranks);
 int p252_dist_finalize(p252_ctx* ctx);
+/* The partition p252_merkle4_build_dist follows (pure host arithmetic, no GPU needed): for every internal
+ * level, bottom-up, where it lives in nodes_out, which slice this rank computes, and whether the level is
+ * all-gathered (sharded = 1) or computed redundantly by every rank (levels with fewer nodes than ranks). */
+typedef struct p252_level_plan {
+    uint64_t level_offset; /* first node of the level inside nodes_out            */
+    uint64_t level_size;   /* nodes in the level                                   */
+    uint64_t my_offset;    /* first node (within the level) this rank computes     */
+    uint64_t my_count;     /* how many it computes                                 */
+    int32_t sharded;       /* 1: slices + all-gather; 0: every rank computes all   */
+    int32_t reserved;
+} p252_level_plan;
+int p252_merkle4_shard_plan(size_t n_leaves_total, int nranks, int rank, p252_level_plan* levels, int capacity,
+                            int* n_levels);
 /* leaves_shard: this rank's contiguous n_leaves_total/nranks leaves (DEVICE or HOST per flags).
  * Every level's output is sharded contiguously across ranks, computed, then all-gathered so that
  * each rank ends with the complete level (levels smaller than nranks are computed redundantly).

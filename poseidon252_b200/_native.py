@@ -41,10 +41,18 @@ SIGNATURES = {
     "p252_dist_unique_id": (c_int, [c_void_p]),
     "p252_dist_init": (c_int, [c_void_p, c_void_p, c_int, c_int]),
     "p252_dist_finalize": (c_int, [c_void_p]),
+    "p252_merkle4_shard_plan": (c_int, [c_size_t, c_int, c_int, c_void_p, c_int, ctypes.POINTER(c_int)]),
     "p252_merkle4_build_dist": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p, c_int]),
 }
 
 MEM_HOST, MEM_DEVICE, ASYNC = 0, 1, 2
+
+
+class LevelPlan(ctypes.Structure):
+    """p252_level_plan"""
+    _fields_ = [("level_offset", ctypes.c_uint64), ("level_size", ctypes.c_uint64), ("my_offset", ctypes.c_uint64),
+                ("my_count", ctypes.c_uint64), ("sharded", ctypes.c_int32), ("reserved", ctypes.c_int32)]
+
 NCCL_UNIQUE_ID_BYTES = 128
 
 

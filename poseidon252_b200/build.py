@@ -47,7 +47,8 @@ def build(force=False, verbose=False):
         return LIB
     generate()
     os.makedirs(os.path.dirname(LIB), exist_ok=True)
-    cmd = [nvcc()] + NVCC_FLAGS + ["-o", LIB] + SOURCES + ["-ldl"]
+    extra = os.environ.get("P252_NVCC_EXTRA", "").split()
+    cmd = [nvcc()] + NVCC_FLAGS + extra + ["-o", LIB] + SOURCES + ["-ldl"]
     res = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     log = os.path.join(PKG, "lib", "build.log")
     with open(log, "w") as f:

@@ -629,59 +629,80 @@ int p252_dist_finalize(p252_ctx* ctx) {
     return P252_OK;
 }
 
-// Contiguous sharding: rank r owns nodes [r*M/G, (r+1)*M/G) of every level with M >= G nodes, whose
+// Contiguous sharding: rank r owns nodes [r*M/G, (r+1)*M/G) of every level with M % G == 0 nodes, whose
 // children are exactly rank r's slice of the level below -- so the compute stream climbs its own
 // subtree without waiting, while the all-gather of each finished level (the level's replication to
-// all GPUs over NVLink) runs on a second stream.  Levels with M < G nodes are computed redundantly
-// by every rank from the gathered level below.
+// all GPUs over NVLink) runs on a second stream.  Smaller levels are computed redundantly by every
+// rank from the gathered level below.
+int p252_merkle4_shard_plan(size_t n_leaves_total, int nranks, int rank, p252_level_plan* levels, int capacity,
+                            int* n_levels) {
+    if (nranks < 1 || rank < 0 || rank >= nranks) return P252_ERR_INVALID_ARGUMENT;
+    int lv = 0;
+    int rc = p252_merkle4_tree_nodes(n_leaves_total, nullptr, &lv);
+    if (rc != P252_OK) return rc;
+    if (n_leaves_total % (size_t)nranks || (n_leaves_total / nranks) % 4) return P252_ERR_INVALID_ARGUMENT;
+    if (n_levels) *n_levels = lv;
+    if (!levels) return P252_OK;
+    if (capacity < lv) return P252_ERR_INVALID_ARGUMENT;
+    uint64_t off = 0, m = n_leaves_total / 4;
+    for (int l = 0; l < lv; ++l, m /= 4) {
+        p252_level_plan& p = levels[l];
+        p.level_offset = off;
+        p.level_size = m;
+        p.sharded = (m % (uint64_t)nranks == 0) ? 1 : 0;
+        p.my_count = p.sharded ? m / nranks : m;
+        p.my_offset = p.sharded ? (uint64_t)rank * p.my_count : 0;
+        p.reserved = 0;
+        off += m;
+    }
+    return P252_OK;
+}
+
 int p252_merkle4_build_dist(p252_ctx* ctx, const p252_fr* leaves_shard, size_t n_leaves_total, p252_fr* nodes_out,
                             int flags) {
     if (!ctx || !leaves_shard || !nodes_out) return P252_ERR_INVALID_ARGUMENT;
     if (!(flags & P252_MEM_DEVICE)) return P252_ERR_INVALID_ARGUMENT;   // shards live on the GPU
     if (!aligned16(leaves_shard) || !aligned16(nodes_out)) return P252_ERR_INVALID_ARGUMENT;
-    size_t n_internal;
-    int rc = p252_merkle4_tree_nodes(n_leaves_total, &n_internal, nullptr);
-    if (rc != P252_OK) return rc;
     const int G = ctx->nranks, r = ctx->rank;
     if (G > 1 && !ctx->comm) return P252_ERR_INVALID_ARGUMENT;
-    if (n_leaves_total % (size_t)G || (n_leaves_total / G) % 4) return P252_ERR_INVALID_ARGUMENT;
+    p252_level_plan plan[64];
+    int lv = 0;
+    int rc = p252_merkle4_shard_plan(n_leaves_total, G, r, plan, 64, &lv);
+    if (rc != P252_OK) return rc;
     DeviceGuard g(ctx->device);
     p252_fr tag;
     p252_hash_tag(P252_DOMAIN_MERKLE4, 4, 1, &tag);
 
-    const p252_fr* below_full = nullptr;   // complete level below (valid once gathered)
+    const p252_fr* below_full = nullptr;        // complete level below (valid once gathered)
     const p252_fr* below_mine = leaves_shard;   // this rank's slice of the level below
-    p252_fr* level = nodes_out;
-    bool gathered_below = true;   // leaves: only the shard is ever needed
+    bool gather_in_flight = false;
     CU(cudaEventRecord(ctx->ev_comm, ctx->stream));
-    for (size_t m = n_leaves_total / 4;; m /= 4) {
-        if (m % (size_t)G == 0) {
-            const size_t cnt = m / G;
-            cudaError_t le = p252::launch_digest(limbs(&tag), below_mine, cnt, 4, level + (size_t)r * cnt, 1, ctx->stream);
+    for (int l = 0; l < lv; ++l) {
+        const p252_level_plan& p = plan[l];
+        p252_fr* level = nodes_out + p.level_offset;
+        if (p.sharded) {
+            // the first level is always sharded (n_leaves_total / G is a multiple of 4)
+            cudaError_t le = p252::launch_digest(limbs(&tag), below_mine, p.my_count, 4, level + p.my_offset, 1, ctx->stream);
             if (le != cudaSuccess) return fail_cuda(ctx, le, "kernel launch");
             ctx->launches++;
             if (G > 1) {
                 CU(cudaEventRecord(ctx->ev_level, ctx->stream));
                 CU(cudaStreamWaitEvent(ctx->comm_stream, ctx->ev_level, 0));
-                NC(nccl().AllGather(level + (size_t)r * cnt, level, cnt * 4, ncclUint64, ctx->comm, ctx->comm_stream));
+                NC(nccl().AllGather(level + p.my_offset, level, p.my_count * 4, ncclUint64, ctx->comm, ctx->comm_stream));
                 CU(cudaEventRecord(ctx->ev_comm, ctx->comm_stream));
-                gathered_below = false;   // in flight
+                gather_in_flight = true;
             }
-            below_mine = level + (size_t)r * cnt;
+            below_mine = level + p.my_offset;
         } else {
-            // small level: needs the complete level below on this rank
-            if (!gathered_below) {
+            if (gather_in_flight) {   // needs the complete level below on this rank
                 CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_comm, 0));
-                gathered_below = true;
+                gather_in_flight = false;
             }
-            cudaError_t le = p252::launch_digest(limbs(&tag), below_full, m, 4, level, 1, ctx->stream);
+            cudaError_t le = p252::launch_digest(limbs(&tag), below_full, p.level_size, 4, level, 1, ctx->stream);
             if (le != cudaSuccess) return fail_cuda(ctx, le, "kernel launch");
             ctx->launches++;
-            below_mine = level;   // unused from here on
         }
         below_full = level;
-        level += m;
-        if (m == 1) break;
     }
     // every level must be complete on every rank before the call is considered done
     CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_comm, 0));

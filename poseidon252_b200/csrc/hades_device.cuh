@@ -8,9 +8,9 @@
 // with the bit-exact "scaled lazy" formulation derived in tools/hades_model.py:
 //   * 365 unreduced Montgomery products per permutation (IMAD.WIDE carry chains, fr_ptx.cuh)
 //     instead of the reference's 2000 (dense 25-multiply MDS every round);
-//   * the MDS layer is 25 small-integer (<= 17 bit) multiply-adds per round with plain
-//     mad.wide.u32 (no carries: 5 * 2^17 * 2^32 < 2^64 per 64-bit column) followed by ONE
-//     Montgomery row per lane; round constants ride inside that same accumulation;
+//   * the MDS layer is 25 small-integer (<= 17 bit) multiply-adds per round, computed EXACTLY in FP64
+//     (DFMA on the otherwise idle FP64 pipe; column sums < 2^52) followed by ONE Montgomery row per
+//     lane; round constants ride inside that same accumulation;
 //   * values stay in [0, 2^256) without modular correction except one predicated subtraction per
 //     S-box (bound analysis: DESIGN.md "Operand bounds").
 // Input and output are BlsScalar.0 (4 x u64 LE limbs, Montgomery form, < p), bit-exact.
@@ -24,7 +24,7 @@ namespace p252 {
 #include "hades_tables.inc"
 
 // hades_tables.inc defines, in the constant bank (statically initialised at module load):
-//   kA[68][5][8]  per-round additive constants (scaled)      kG[60][8]  lane-4 correction
+//   kA0[5][8], kA[69][5][9]  per-round additive constants (scaled)   kG[60][8]  lane-4 correction
 //   kF[8]         final multiplier                           kDenseArc / kDenseMds  dense tables
 // Every thread of a warp reads the same word in the same instruction (the round index is
 // warp-uniform), which the constant cache serves as a broadcast operand.
@@ -69,52 +69,59 @@ __device__ __forceinline__ void load_const(uint32_t (&d)[8], const uint32_t* c) 
     for (int k = 0; k < 8; ++k) d[k] = c[k];
 }
 
-// One lane of the MDS layer: t = sum_j C[i][j] * z[j] as even/odd 64-bit column sums.
-template <int I>
-__device__ __forceinline__ void mix_lane(uint32_t (&t)[9], const uint32_t (&z)[5][8]) {
-    uint64_t e[4], o[4];
+// One lane of the MDS layer: t = sum_j C[i][j] * z[j].
+//
+// The 25 products per round are (<= 17 bit constant) x (32-bit limb); a column sum over the five lanes is
+// below 268697 * 2^32 < 2^50.1, i.e. EXACT in an IEEE double.  B200 has a full-rate FP64 pipe that the
+// integer kernel leaves idle, so the column sums are formed with DFMA on that pipe (concurrently with the
+// IMAD.WIDE carry chains of the S-box on the fmaheavy pipe) instead of 40 IMAD.WIDE per lane:
+//   limb -> double : bit-pattern trick, (2^52 | limb) - 2^52 (one DADD, exact)
+//   acc = 2^52 + sum_j c_ij * limb_j  (five DFMA, every partial sum is an integer < 2^53: no rounding)
+//   column = mantissa bits of acc (low word | 20 bits of the high word).
+// zd[j][k] holds limb k of lane j as a double.
+constexpr double kTwo52 = 4503599627370496.0;
+
+// s <- redc1(C s + A[next_round]) in place -- mul_matrix (+ the next add_round_constants) of the reference,
+// /root/reference/src/hades/permutation/scalar.rs:39-48,54-64.
+//
+// The 25 products per round are (<= 17 bit constant) x (32-bit limb); a column sum over the five lanes is
+// below 268697 * 2^32 < 2^50.1, i.e. EXACT in an IEEE double.  B200 has a full-rate FP64 pipe that the integer
+// S-box leaves idle, so the column sums are formed with DFMA there (concurrently with the IMAD.WIDE carry
+// chains on the fmaheavy pipe) instead of 40 IMAD.WIDE per lane:
+//   limb -> double      : I2F.F64.U32 (exact)
+//   acc = 2^52 + sum_j c_ij * limb_j   (five DFMA; every partial sum is an integer < 2^53: no rounding)
+//   raw bits of acc     = 0x43300000_00000000 + column sum
+// Limb-major: for limb k the five lanes' limbs are converted once and the five raw columns are folded straight
+// into the 9-limb totals t[i] (column k overlaps column k+1 by its upper word).  The exponent words are not
+// masked off: their sum K_off is pre-subtracted (mod 2^288) from the 9-limb round constant kA[next_round][i],
+// and the addition inside fr_arc_redc1 wraps to the true integer C s + A < 2^288.
+__device__ __forceinline__ void mix(uint32_t (&s)[5][8], int next_round) {
+    uint32_t t[5][9];
+    uint32_t hi_prev[5] = {0, 0, 0, 0, 0}, carry[5] = {0, 0, 0, 0, 0};
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        e[k] = (uint64_t)hades_cmat(I, 0) * z[0][2 * k];
-        o[k] = (uint64_t)hades_cmat(I, 0) * z[0][2 * k + 1];
-    }
+    for (int k = 0; k < 8; ++k) {
+        double d[5];
 #pragma unroll
-    for (int j = 1; j < 5; ++j) {
+        for (int j = 0; j < 5; ++j) d[j] = (double)s[j][k];
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            e[k] += (uint64_t)hades_cmat(I, j) * z[j][2 * k];
-            o[k] += (uint64_t)hades_cmat(I, j) * z[j][2 * k + 1];
+        for (int i = 0; i < 5; ++i) {
+            double acc = kTwo52;
+#pragma unroll
+            for (int j = 0; j < 5; ++j) acc = fma((double)hades_cmat(i, j), d[j], acc);
+            const uint64_t sum = (uint64_t)(uint32_t)__double2loint(acc) + hi_prev[i] + carry[i];
+            t[i][k] = (uint32_t)sum;
+            carry[i] = (uint32_t)(sum >> 32);
+            hi_prev[i] = (uint32_t)__double2hiint(acc);
         }
     }
-    uint32_t e32[8], o32[8];
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        e32[2 * k] = (uint32_t)e[k];
-        e32[2 * k + 1] = (uint32_t)(e[k] >> 32);
-        o32[2 * k] = (uint32_t)o[k];
-        o32[2 * k + 1] = (uint32_t)(o[k] >> 32);
+    for (int i = 0; i < 5; ++i) {
+        t[i][8] = hi_prev[i] + carry[i];
+        uint32_t c[9];
+#pragma unroll
+        for (int k = 0; k < 9; ++k) c[k] = kA[next_round][i][k];
+        fr_arc_redc1(s[i], t[i], c);
     }
-    fr_mix_sum(t, e32, o32);
-}
-
-// u = redc1(C z + A[next_round])  -- mul_matrix (+ the next add_round_constants) of the reference,
-// /root/reference/src/hades/permutation/scalar.rs:39-48,54-64.  next_round < 0: no constants.
-__device__ __forceinline__ void mix(uint32_t (&u)[5][8], const uint32_t (&z)[5][8], int next_round) {
-    uint32_t t[9], c[8];
-#define P252_MIX_LANE(I)                              \
-    mix_lane<I>(t, z);                                \
-    if (next_round >= 0) {                            \
-        load_const(c, kA[next_round][I]);             \
-        fr_arc_redc1(u[I], t, c);                     \
-    } else {                                          \
-        fr_redc1(u[I], t);                            \
-    }
-    P252_MIX_LANE(0)
-    P252_MIX_LANE(1)
-    P252_MIX_LANE(2)
-    P252_MIX_LANE(3)
-    P252_MIX_LANE(4)
-#undef P252_MIX_LANE
 }
 
 // In-register Hades permutation, standard Montgomery form in and out (both < p).
@@ -123,23 +130,24 @@ __device__ __forceinline__ void hades_permute(uint32_t (&s)[5][8]) {
     // first add_round_constants: explicit, then one full conditional subtraction
 #pragma unroll
     for (int i = 0; i < 5; ++i) {
-        load_const(c, kA[0][i]);
+        load_const(c, kA0[i]);
         uint32_t t[8];
         fr_add_lazy(t, s[i], c);
         fr_condsub(t);
 #pragma unroll
         for (int k = 0; k < 8; ++k) s[i][k] = t[k];
     }
-    uint32_t z[5][8];
 #pragma unroll 1
     for (int r = 0; r < kRounds; ++r) {
         const bool full = (r < kHalfFull) || (r >= kHalfFull + kPartial);
-        if (full) {
-            // S-box on every lane: process slot 4 and rotate, so that one code instance serves all
+        // One S-box code instance serves both round kinds: it always works on slot 4.  Full rounds run it five
+        // times, rotating the lanes through slot 4; partial rounds run it once and apply the lane-4 correction.
+        const int n_sbox = full ? 5 : 1;
 #pragma unroll 1
-            for (int it = 0; it < 5; ++it) {
-                uint32_t w[8];
-                sbox(w, s[4]);
+        for (int it = 0; it < n_sbox; ++it) {
+            uint32_t w[8];
+            sbox(w, s[4]);
+            if (full) {
 #pragma unroll
                 for (int k = 0; k < 8; ++k) {
                     s[4][k] = s[3][k];
@@ -148,22 +156,12 @@ __device__ __forceinline__ void hades_permute(uint32_t (&s)[5][8]) {
                     s[1][k] = s[0][k];
                     s[0][k] = w[k];
                 }
+            } else {
+                load_const(c, kG[r - kHalfFull]);
+                montmul(s[4], c, w);
             }
-#pragma unroll
-            for (int i = 0; i < 5; ++i)
-#pragma unroll
-                for (int k = 0; k < 8; ++k) z[i][k] = s[i][k];
-        } else {
-            uint32_t w[8];
-            sbox(w, s[4]);
-            load_const(c, kG[r - kHalfFull]);
-            montmul(z[4], c, w);
-#pragma unroll
-            for (int i = 0; i < 4; ++i)
-#pragma unroll
-                for (int k = 0; k < 8; ++k) z[i][k] = s[i][k];
         }
-        mix(s, z, (r + 1 < kRounds) ? (r + 1) : -1);
+        mix(s, r + 1);      // r + 1 == kRounds: row 68 of kA carries no round constants
     }
     // leave the scaled domain: out = montmul(F, v) fully reduced
     load_const(c, kF);

@@ -15,7 +15,11 @@
 
 namespace p252 {
 
+#ifndef P252_MINBLOCKS
+#define P252_MINBLOCKS 5      // resident 128-thread blocks per SM the register allocation is held to (<= 102 regs)
+#endif
 constexpr int kThreads = 128;
+constexpr int kMinBlocks = P252_MINBLOCKS;
 constexpr int kWarps = kThreads / 32;
 
 struct FrArg {
@@ -73,7 +77,7 @@ __device__ __forceinline__ void warp_scatter(uint4 (*st)[8], uint8_t* base, size
 // One permutation call site: step s > 0 is always preceded by a permutation; steps [0, nin) absorb
 // 4-scalar chunks, steps [nin, nin+nout) squeeze 4-scalar chunks.  Permutations = nin + nout - 1
 // = ceil(in_len/4) + ceil(out_len/4) - 1  (Merkle4: exactly 1).
-__global__ void __launch_bounds__(kThreads) k_sponge_digest(FrArg tag, const uint8_t* __restrict__ in, size_t n,
+__global__ void __launch_bounds__(kThreads, kMinBlocks) k_sponge_digest(FrArg tag, const uint8_t* __restrict__ in, size_t n,
                                                             uint32_t in_len, uint8_t* __restrict__ out,
                                                             uint32_t out_len) {
     __shared__ uint4 stage[kWarps][32][8];
@@ -126,7 +130,7 @@ __global__ void __launch_bounds__(kThreads) k_sponge_digest(FrArg tag, const uin
 
 // ---- raw permutation of n x 5 states in place (Safe::permute) -----------------------------------
 template <bool kDense>
-__global__ void __launch_bounds__(kThreads) k_permute(uint8_t* __restrict__ states, size_t n) {
+__global__ void __launch_bounds__(kThreads, kDense ? 1 : kMinBlocks) k_permute(uint8_t* __restrict__ states, size_t n) {
     __shared__ uint4 stage[kWarps][32][8];
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
@@ -183,7 +187,7 @@ __device__ __forceinline__ void store_fr(uint8_t* p, const uint32_t (&d)[8]) {
 }
 
 template <bool kDecrypt>
-__global__ void __launch_bounds__(kThreads) k_crypt(FrArg tag, const uint8_t* __restrict__ src, size_t n, uint32_t L,
+__global__ void __launch_bounds__(kThreads, kMinBlocks) k_crypt(FrArg tag, const uint8_t* __restrict__ src, size_t n, uint32_t L,
                                                     const uint8_t* __restrict__ secret_uv,
                                                     const uint8_t* __restrict__ nonce, uint8_t* dst,
                                                     uint8_t* __restrict__ ok) {

@@ -25,3 +25,18 @@ def level_offsets(n_leaves):
             break
         m //= 4
     return out
+
+
+def shard_plan(n_leaves_total, nranks, rank):
+    """The per-level partition of the multi-GPU build (p252_merkle4_shard_plan): list of dicts with
+    level_offset, level_size, my_offset, my_count, sharded -- bottom-up."""
+    import ctypes
+
+    from . import _native
+    from .errors import raise_for_status
+    lib = _native.lib()
+    n = ctypes.c_int(0)
+    raise_for_status(lib.p252_merkle4_shard_plan(int(n_leaves_total), int(nranks), int(rank), None, 0, ctypes.byref(n)), lib)
+    arr = (_native.LevelPlan * n.value)()
+    raise_for_status(lib.p252_merkle4_shard_plan(int(n_leaves_total), int(nranks), int(rank), arr, n.value, ctypes.byref(n)), lib)
+    return [{f: int(getattr(a, f)) for f in ("level_offset", "level_size", "my_offset", "my_count", "sharded")} for a in arr]

@@ -57,19 +57,23 @@ def test_montsqr_and_wide_reduction():
 
 
 def test_mix_tail():
+    """FP64 column sums (exact, < 2^52) folded with their exponent words + wrap-around constant + one
+    Montgomery row == redc1(C z + A)."""
     rnd = random.Random(2)
     for _ in range(500):
-        z = [rnd.randrange(int(1.8 * hm.P)) for _ in range(5)]
+        z = [rnd.randrange(int(1.9 * hm.P)) for _ in range(5)]
         if rnd.random() < 0.3:
-            z = [int(1.8 * hm.P) - rnd.randrange(1 << 40) for _ in range(5)]
+            z = [int(1.9 * hm.P) - rnd.randrange(1 << 40) for _ in range(5)]
+        if rnd.random() < 0.1:
+            z = [hm.TWO256 - 1 - rnd.randrange(1 << 20) for _ in range(5)]      # all-ones limbs: largest columns
         i = rnd.randrange(5)
         arc = rnd.choice([None, rnd.randrange(hm.P), hm.P - 1])
         zl = [hm.limbs32(v) for v in z]
-        e = [sum(hm.CMAT[i][j] * zl[j][2 * k] for j in range(5)) for k in range(4)]
-        o = [sum(hm.CMAT[i][j] * zl[j][2 * k + 1] for j in range(5)) for k in range(4)]
-        assert all(c < (1 << 64) for c in e + o)          # plain mad.wide never overflows a column
+        cols = [sum(hm.CMAT[i][j] * zl[j][k] for j in range(5)) for k in range(8)]
+        for c in cols:                                   # exact in an IEEE double next to the 2^52 bias
+            assert c < (1 << 52) and int(float((1 << 52) + c)) == (1 << 52) + c
         t = sum(hm.CMAT[i][j] * z[j] for j in range(5)) + (arc or 0)
-        assert g.emu_mix_lane(e, o, arc) == hm.redc1(t)
+        assert g.emu_mix_lane(cols, arc) == hm.redc1(t)
 
 
 def test_conditional_subtractions_and_addsub():

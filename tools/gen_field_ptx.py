@@ -251,16 +251,19 @@ def gen_mix_sum() -> Prog:
 
 
 def gen_redc1(with_arc: bool) -> Prog:
+    """t (9 limbs) holds the folded FP64 column sums INCLUDING the double-exponent offsets
+    K_off = 0x43300000 * sum_{k=1..8} 2^(32k); a (9 limbs) = (A - K_off) mod 2^288, so that t + a wraps to the
+    true T + A < 2^288.  Then one Montgomery row."""
     name = "fr_arc_redc1" if with_arc else "fr_redc1"
-    pg = Prog(name, "u = (t (+ a) + m p) >> 32 with m = -(t+a) mod 2^32; t is 9 limbs")
+    pg = Prog(name, "u = (t + a (mod 2^288) + m p) >> 32 with m = -(t+a) mod 2^32; t, a are 9 limbs")
     u = pg.out(*arr("u", 8))
     t = pg.inout(*arr("t", 9))
     if with_arc:
-        a = pg.inp(*arr("a", 8))
+        a = pg.inp(*arr("a", 9))
         pg.op("add.cc.u32", t[0], t[0], a[0])
         for k in range(1, 8):
             pg.op("addc.cc.u32", t[k], t[k], a[k])
-        pg.op("addc.u32", t[8], t[8], 0, nocarry=True)
+        pg.op("addc.u32", t[8], t[8], a[8])          # wraps mod 2^288 by construction
     m, junk = pg.tmp("m", "junk")
     pg.op("sub.u32", m, 0, t[0])
     pg.op("add.cc.u32", junk, t[0], m)                       # carry = (t0 != 0)
@@ -491,7 +494,7 @@ def gen_redc_wide() -> Prog:
     return pg
 
 
-ALL = [gen_row_first(), gen_row(), gen_merge(), gen_mix_sum(), gen_redc1(True), gen_redc1(False),
+ALL = [gen_row_first(), gen_row(), gen_merge(), gen_redc1(True),
        gen_condsub255(), gen_condsub(), gen_add(), gen_submod(),
        gen_sqr_product(), gen_redc_wide()]
 BY_NAME = {p.name: p for p in ALL}
@@ -500,9 +503,7 @@ SIGS = {
     "fr_row_first": "uint32_t (&ev)[8], uint32_t (&od)[8], const uint32_t (&x)[8], uint32_t yi",
     "fr_row": "uint32_t (&ev)[8], uint32_t (&od)[8], const uint32_t (&x)[8], uint32_t yi",
     "fr_merge": "uint32_t (&r)[8], const uint32_t (&ev)[8], const uint32_t (&od)[8]",
-    "fr_mix_sum": "uint32_t (&t)[9], const uint32_t (&e)[8], const uint32_t (&o)[8]",
-    "fr_arc_redc1": "uint32_t (&u)[8], uint32_t (&t)[9], const uint32_t (&a)[8]",
-    "fr_redc1": "uint32_t (&u)[8], uint32_t (&t)[9]",
+    "fr_arc_redc1": "uint32_t (&u)[8], uint32_t (&t)[9], const uint32_t (&a)[9]",
     "fr_condsub255": "uint32_t (&a)[8]",
     "fr_condsub": "uint32_t (&a)[8]",
     "fr_add_lazy": "uint32_t (&r)[8], const uint32_t (&a)[8], const uint32_t (&b)[8]",
@@ -549,16 +550,23 @@ def emu_redc_wide(t: int) -> int:
     return sum(v << (32 * i) for i, v in enumerate(_get(reg, "r", 8)))
 
 
-def emu_mix_lane(e_cols: Sequence[int], o_cols: Sequence[int], arc: int | None) -> int:
-    """e_cols/o_cols: the four 64-bit column sums of the even / odd limbs."""
-    e = [(c >> (32 * h)) & M32 for c in e_cols for h in (0, 1)]
-    o = [(c >> (32 * h)) & M32 for c in o_cols for h in (0, 1)]
-    reg = BY_NAME["fr_mix_sum"].run({**_put("e", e), **_put("o", o)})
-    t = _get(reg, "t", 9)
-    if arc is None:
-        reg = BY_NAME["fr_redc1"].run(_put("t", t))
-    else:
-        reg = BY_NAME["fr_arc_redc1"].run({**_put("t", t), **_put("a", [(arc >> (32 * i)) & M32 for i in range(8)])})
+K_OFF = 0x43300000 * sum(1 << (32 * k) for k in range(1, 9))     # exponent words of the 8 double columns
+
+
+def emu_mix_lane(cols: Sequence[int], arc: int | None) -> int:
+    """cols[k]: the exact column sum of limb k (< 2^52), as produced by the DFMA chain.  Mirrors the CUDA mix:
+    raw = bits(2^52 + col) ; t[k] = lo_k + hi_raw_{k-1} + carry ; then fr_arc_redc1 with a = A - K_off."""
+    t, hi_prev, carry = [], 0, 0
+    for k in range(8):
+        assert 0 <= cols[k] < (1 << 52)
+        raw = 0x4330000000000000 + cols[k]
+        sm = (raw & M32) + hi_prev + carry
+        t.append(sm & M32)
+        carry = sm >> 32
+        hi_prev = raw >> 32
+    t.append((hi_prev + carry) & M32)
+    a = ((arc or 0) - K_OFF) % (1 << 288)
+    reg = BY_NAME["fr_arc_redc1"].run({**_put("t", t), **_put("a", [(a >> (32 * i)) & M32 for i in range(9)])})
     return sum(v << (32 * i) for i, v in enumerate(_get(reg, "u", 8)))
 
 

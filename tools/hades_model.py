@@ -41,6 +41,8 @@ LAMBDA = lcm(*range(WIDTH, 3 * WIDTH - 1))          # lcm(5..13) = 360360
 CMAT = [[LAMBDA // (i + j + WIDTH) for j in range(WIDTH)] for i in range(WIDTH)]
 M32 = (1 << 32) - 1
 TWO256 = 1 << 256
+# exponent words (0x433 << 20) of the eight IEEE-double column sums the FP64 mix folds into 9 limbs
+K_OFF = 0x43300000 * sum(1 << (32 * k) for k in range(1, 9))
 
 
 def inv(x: int) -> int:
@@ -174,7 +176,12 @@ def sbox(u: int) -> int:
 
 def mix(z: Sequence[int], arc_next: Sequence[int] | None) -> List[int]:
     out = []
+    zl = [limbs32(v) for v in z]
     for i in range(WIDTH):
+        # every limb column must be exact in an IEEE double next to the 2^52 bias (FP64-pipe mix)
+        for k in range(8):
+            col = sum(CMAT[i][j] * zl[j][k] for j in range(WIDTH))
+            assert col < (1 << 52) and float(col + (1 << 52)) == col + (1 << 52)
         t = sum(CMAT[i][j] * z[j] for j in range(WIDTH))
         if arc_next is not None:
             t += arc_next[i]
