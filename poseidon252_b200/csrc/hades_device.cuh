@@ -24,7 +24,7 @@ namespace p252 {
 #include "hades_tables.inc"
 
 // hades_tables.inc defines, in the constant bank (statically initialised at module load):
-//   kA0[5][8], kA[69][5][9]  per-round additive constants (scaled)   kG[60][8]  lane-4 correction
+//   kA0[5][8], kA[69][5][12]  per-round additive constants (scaled)   kG[60][8]  lane-4 correction
 //   kF[8]         final multiplier                           kDenseArc / kDenseMds  dense tables
 // Every thread of a warp reads the same word in the same instruction (the round index is
 // warp-uniform), which the constant cache serves as a broadcast operand.

@@ -253,7 +253,9 @@ def gen_mix_sum() -> Prog:
 def gen_redc1(with_arc: bool) -> Prog:
     """t (9 limbs) holds the folded FP64 column sums INCLUDING the double-exponent offsets
     K_off = 0x43300000 * sum_{k=1..8} 2^(32k); a (9 limbs) = (A - K_off) mod 2^288, so that t + a wraps to the
-    true T + A < 2^288.  Then one Montgomery row."""
+    true T + A < 2^288.  Then one Montgomery row, kept in even/odd form so that every IMAD.WIDE accumulator is
+    one fixed (even, odd) register pair: the even products m*p2, m*p4, m*p6 chain into t itself, the odd
+    products m*p1..p7 go to a fresh odd-aligned array (plain mul.wide), and one add chain merges them."""
     name = "fr_arc_redc1" if with_arc else "fr_redc1"
     pg = Prog(name, "u = (t + a (mod 2^288) + m p) >> 32 with m = -(t+a) mod 2^32; t, a are 9 limbs")
     u = pg.out(*arr("u", 8))
@@ -264,20 +266,22 @@ def gen_redc1(with_arc: bool) -> Prog:
         for k in range(1, 8):
             pg.op("addc.cc.u32", t[k], t[k], a[k])
         pg.op("addc.u32", t[8], t[8], a[8])          # wraps mod 2^288 by construction
-    m, junk = pg.tmp("m", "junk")
+    m = pg.tmp("m")
+    o = pg.tmp(*["o%d" % k for k in range(1, 9)])     # o[k-1] <-> limb k
     pg.op("sub.u32", m, 0, t[0])
-    pg.op("add.cc.u32", junk, t[0], m)                       # carry = (t0 != 0)
-    for k in (0, 2, 4):
-        pg.op("madc.lo.cc.u32", u[k], m, PL[k + 1], t[k + 1])
-        pg.op("madc.hi.cc.u32", u[k + 1], m, PL[k + 1], t[k + 2])
-    pg.op("madc.lo.cc.u32", u[6], m, PL[7], t[7])
-    pg.op("madc.hi.u32", u[7], m, PL[7], t[8], nocarry=True)
-    pg.op("mad.lo.cc.u32", u[1], m, PL[2], u[1])
-    pg.op("madc.hi.cc.u32", u[2], m, PL[2], u[2])
-    for k in (3, 5):
-        pg.op("madc.lo.cc.u32", u[k], m, PL[k + 1], u[k])
-        pg.op("madc.hi.cc.u32", u[k + 1], m, PL[k + 1], u[k + 1])
-    pg.op("addc.u32", u[7], u[7], 0, nocarry=True)
+    for idx, pj in enumerate((1, 3, 5, 7)):           # odd columns (1,2),(3,4),(5,6),(7,8): fresh
+        pg.op("mul.lo.u32", o[2 * idx], m, PL[pj])
+        pg.op("mul.hi.u32", o[2 * idx + 1], m, PL[pj])
+    pg.op("add.cc.u32", t[0], t[0], m)                # limb 0 cancels; carry = (t0 != 0)
+    pg.op("addc.cc.u32", t[1], t[1], 0)
+    for k in (2, 4, 6):                               # even columns (2,3),(4,5),(6,7)
+        pg.op("madc.lo.cc.u32", t[k], m, PL[k], t[k])
+        pg.op("madc.hi.cc.u32", t[k + 1], m, PL[k], t[k + 1])
+    pg.op("addc.u32", t[8], t[8], 0, nocarry=True)
+    pg.op("add.cc.u32", u[0], t[1], o[0])
+    for k in range(1, 7):
+        pg.op("addc.cc.u32", u[k], t[k + 1], o[k])
+    pg.op("addc.u32", u[7], t[8], o[7], nocarry=True)
     return pg
 
 
