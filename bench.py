@@ -150,7 +150,7 @@ def cpu_baseline_block(target_seconds=10.0):
                       "(oracle/hades_ref.c, 4x64-bit Montgomery), %d pthreads, %.1f s" % (n, threads, dt)}
 
 
-def run_reference_arm(args, rank, world):
+def run_reference_arm(args, rank, world, emit):
     if rank != 0:
         return
     threads = usable_cores()
@@ -173,7 +173,7 @@ def run_reference_arm(args, rank, world):
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
                              "sample": "%d digests per step x %d steps, %d pthreads" % (per_step, args.steps, threads)},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ---------------------------------------------------------------------------------------------------------
@@ -192,8 +192,18 @@ def main():
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     rank, world, local = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
 
+    # Exactly ONE line may reach stdout (the JSON); native libraries (e.g. NCCL's version banner) write to
+    # fd 1 too, so fd 1 is pointed at stderr for the duration of the run and the JSON goes to the saved fd.
+    sys.stdout.flush()
+    real_stdout = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+
+    def emit(obj):
+        real_stdout.write(json.dumps(obj) + "\n")
+        real_stdout.flush()
+
     if args.impl == "reference":
-        run_reference_arm(args, rank, world)
+        run_reference_arm(args, rank, world, emit)
         return
 
     import numpy as np
@@ -364,7 +374,7 @@ def main():
             line["cpu_baseline"] = cpu_baseline_block()
         except Exception as exc:  # the oracle is only a reported baseline; never hide the GPU number
             line["cpu_baseline"] = {"error": repr(exc)}
-    print(json.dumps(line), flush=True)
+    emit(line)
     if dist is not None:
         dist.destroy_process_group()
 
