@@ -18,7 +18,10 @@ namespace p252 {
 #ifndef P252_MINBLOCKS
 #define P252_MINBLOCKS 5      // resident 128-thread blocks per SM the register allocation is held to (<= 102 regs)
 #endif
-constexpr int kThreads = 128;
+#ifndef P252_THREADS
+#define P252_THREADS 128
+#endif
+constexpr int kThreads = P252_THREADS;
 constexpr int kMinBlocks = P252_MINBLOCKS;
 constexpr int kWarps = kThreads / 32;
 

@@ -24,6 +24,9 @@ from hades_model import P, M32  # noqa: E402
 
 PL = [(P >> (32 * i)) & M32 for i in range(8)]
 assert PL[0] == 1 and PL[1] == M32
+# p1 = 2^32 - 1: m*p1 = (m << 32) - m, i.e. lo = -m = w0 (the limb being cancelled) and hi = m - (m != 0).
+# With P1_ALU the two halves are formed on the ALU pipe (borrow of 0 - w0) instead of an IMAD.HI.
+P1_ALU = os.environ.get("P252_P1_ALU", "0") == "1"
 
 Operand = Union[str, int]
 
@@ -88,6 +91,9 @@ class Prog:
                 continue
             if base == "and":
                 reg[d] = val(src[0]) & val(src[1])
+                continue
+            if base == "min":
+                reg[d] = min(val(src[0]), val(src[1]))
                 continue
             if base == "shf":           # shf.l.wrap.b32 d, lo, hi, n : upper word of (hi:lo) << n
                 n = val(src[2]) & 31
@@ -164,10 +170,19 @@ def arr(name: str, n: int) -> List[str]:
 # Needs x + p <= 2^256 (window stays below 2^288); y is arbitrary (< 2^256).
 # ------------------------------------------------------------------------------------------------
 def _reduce_row(pg: Prog, ev, od, m):
-    pg.op("sub.u32", m, 0, ev[0])                                   # m = -W mod 2^32
-    # odd columns (1,2),(3,4),(5,6),(7,8) += m * p1,p3,p5,p7
-    pg.op("mad.lo.cc.u32", od[0], m, PL[1], od[0])
-    pg.op("madc.hi.cc.u32", od[1], m, PL[1], od[1])
+    if P1_ALU:
+        h = m + "h"
+        if h not in pg.temps:
+            pg.tmp(h)
+        pg.op("sub.cc.u32", m, 0, ev[0])                            # m = -W mod 2^32, borrow = (W0 != 0)
+        pg.op("subc.u32", h, m, 0)                                  # hi(m * p1) = m - (m != 0)
+        pg.op("add.cc.u32", od[0], od[0], ev[0])                    # lo(m * p1) = -m = W0
+        pg.op("addc.cc.u32", od[1], od[1], h)
+    else:
+        pg.op("sub.u32", m, 0, ev[0])                               # m = -W mod 2^32
+        # odd columns (1,2),(3,4),(5,6),(7,8) += m * p1,p3,p5,p7
+        pg.op("mad.lo.cc.u32", od[0], m, PL[1], od[0])
+        pg.op("madc.hi.cc.u32", od[1], m, PL[1], od[1])
     for k in (2, 4):
         pg.op("madc.lo.cc.u32", od[k], m, PL[k + 1], od[k])
         pg.op("madc.hi.cc.u32", od[k + 1], m, PL[k + 1], od[k + 1])
@@ -459,8 +474,25 @@ def gen_redc_wide() -> Prog:
             cf = True
         m = fresh("m")
         pg.op("sub.u32", m, 0, EV[0])
+        odd_cols = (0, 2, 4, 6)
+        if P1_ALU:
+            # m * p1 = (EV0, m - (m != 0)) formed without the multiplier and without touching the carry flag
+            one, h = fresh("c"), fresh("h")
+            pg.op("min.u32", one, m, 1)
+            pg.op("sub.u32", h, m, one)
+            for kk, val in ((0, EV[0]), (1, h)):
+                if OD[kk] is not None or cf:
+                    src = OD[kk] if OD[kk] is not None else 0
+                    if OD[kk] is None:
+                        OD[kk] = fresh("w")
+                    pg.op("addc.cc.u32" if cf else "add.cc.u32", OD[kk], src, val)
+                    cf = True
+                else:
+                    OD[kk] = fresh("w")
+                    pg.op("mov.u32", OD[kk], val)
+            odd_cols = (2, 4, 6)
         # odd columns += m * (p1, p3, p5, p7)
-        for idx, k in enumerate((0, 2, 4, 6)):
+        for idx, k in enumerate(odd_cols):
             pj = PL[k + 1]
             for half, kk in (("lo", k), ("hi", k + 1)):
                 last = (kk == 7)
