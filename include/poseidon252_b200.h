@@ -123,6 +123,17 @@ int p252_digest_batch(p252_ctx* ctx, const p252_fr* tag, const p252_fr* in, size
 int p252_hash_batch(p252_ctx* ctx, int domain, const p252_fr* in, size_t n, size_t in_len, p252_fr* out,
                     size_t out_len, int flags);
 
+/* Hash::digest_truncated batch (src/hash.rs:164-183,203-210): every output scalar is taken out of Montgomery
+ * form and masked to 250 bits; out_raw receives the raw limbs the reference passes to JubJubScalar::from_raw. */
+int p252_hash_batch_truncated(p252_ctx* ctx, int domain, const p252_fr* in, size_t n, size_t in_len, p252_fr* out_raw,
+                              size_t out_len, int flags);
+
+/* Wire format (BlsScalar::from_bytes / to_bytes as used at src/hades.rs:94-105,131): n canonical 32-byte
+ * little-endian integers <-> BlsScalar.0.  from_bytes: ok[i] = 0 and out[i] = 0 when the value is >= p (the
+ * reference returns None); ok may be NULL. */
+int p252_scalars_from_bytes(p252_ctx* ctx, const uint8_t* bytes, size_t n, p252_fr* out, uint8_t* ok, int flags);
+int p252_scalars_to_bytes(p252_ctx* ctx, const p252_fr* in, size_t n, uint8_t* bytes, int flags);
+
 /* encrypt_batch: n x encrypt(msg[i], (u,v)[i], nonce[i]) (src/encryption.rs:62-74).
  * msg: n x L, secret_uv: n x 2 (JubJubAffine::get_u/get_v), nonce: n, cipher: n x (L+1). */
 int p252_encrypt_batch(p252_ctx* ctx, const p252_fr* msg, size_t n, size_t L, const p252_fr* secret_uv,

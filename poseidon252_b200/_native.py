@@ -32,6 +32,9 @@ SIGNATURES = {
     "p252_permute_batch_dense": (c_int, [c_void_p, c_void_p, c_size_t, c_int]),
     "p252_digest_batch": (c_int, [c_void_p, c_void_p, c_void_p, c_size_t, c_size_t, c_void_p, c_size_t, c_int]),
     "p252_hash_batch": (c_int, [c_void_p, c_int, c_void_p, c_size_t, c_size_t, c_void_p, c_size_t, c_int]),
+    "p252_hash_batch_truncated": (c_int, [c_void_p, c_int, c_void_p, c_size_t, c_size_t, c_void_p, c_size_t, c_int]),
+    "p252_scalars_from_bytes": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p, c_void_p, c_int]),
+    "p252_scalars_to_bytes": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p, c_int]),
     "p252_encrypt_batch": (c_int, [c_void_p, c_void_p, c_size_t, c_size_t, c_void_p, c_void_p, c_void_p, c_int]),
     "p252_decrypt_batch": (c_int, [c_void_p, c_void_p, c_size_t, c_size_t, c_void_p, c_void_p, c_void_p, c_void_p,
                                    ctypes.POINTER(c_size_t), c_int]),

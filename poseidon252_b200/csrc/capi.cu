@@ -427,8 +427,8 @@ int p252_permute_batch_dense(p252_ctx* ctx, p252_fr* states, size_t n, int flags
     return permute_impl(ctx, states, n, flags, true);
 }
 
-int p252_digest_batch(p252_ctx* ctx, const p252_fr* tag, const p252_fr* in, size_t n, size_t in_len, p252_fr* out,
-                      size_t out_len, int flags) {
+static int digest_impl(p252_ctx* ctx, const p252_fr* tag, const p252_fr* in, size_t n, size_t in_len, p252_fr* out,
+                       size_t out_len, int flags, bool truncate) {
     if (!ctx || !tag || ((!in || !out) && n)) return P252_ERR_INVALID_ARGUMENT;
     if (in_len == 0 || out_len == 0) return P252_ERR_INVALID_IO_PATTERN;
     if (in_len > 0x7fffffffull / 32 || out_len > 0x7fffffffull / 32) return P252_ERR_INVALID_ARGUMENT;
@@ -437,12 +437,17 @@ int p252_digest_batch(p252_ctx* ctx, const p252_fr* tag, const p252_fr* in, size
     if (flags & P252_MEM_DEVICE) {
         if (!aligned16(in) || !aligned16(out)) return P252_ERR_INVALID_ARGUMENT;
         if (n == 0) return P252_OK;
-        return finish_device_call(ctx, p252::launch_digest(limbs(tag), in, n, il, out, ol, ctx->stream), flags);
+        return finish_device_call(ctx, p252::launch_digest(limbs(tag), in, n, il, out, ol, truncate, ctx->stream), flags);
     }
     std::vector<Io> ios = {{in, nullptr, in_len * 32}, {nullptr, out, out_len * 32}};
     return run_host_pipeline(ctx, ios, n, [&](void** d, size_t cnt, cudaStream_t st) {
-        return p252::launch_digest(limbs(tag), d[0], cnt, il, d[1], ol, st);
+        return p252::launch_digest(limbs(tag), d[0], cnt, il, d[1], ol, truncate, st);
     });
+}
+
+int p252_digest_batch(p252_ctx* ctx, const p252_fr* tag, const p252_fr* in, size_t n, size_t in_len, p252_fr* out,
+                      size_t out_len, int flags) {
+    return digest_impl(ctx, tag, in, n, in_len, out, out_len, flags, false);
 }
 
 int p252_hash_batch(p252_ctx* ctx, int domain, const p252_fr* in, size_t n, size_t in_len, p252_fr* out,
@@ -450,7 +455,38 @@ int p252_hash_batch(p252_ctx* ctx, int domain, const p252_fr* in, size_t n, size
     p252_fr tag;
     int rc = p252_hash_tag(domain, in_len, out_len, &tag);
     if (rc != P252_OK) return rc;
-    return p252_digest_batch(ctx, &tag, in, n, in_len, out, out_len, flags);
+    return digest_impl(ctx, &tag, in, n, in_len, out, out_len, flags, false);
+}
+
+int p252_hash_batch_truncated(p252_ctx* ctx, int domain, const p252_fr* in, size_t n, size_t in_len, p252_fr* out_raw,
+                              size_t out_len, int flags) {
+    p252_fr tag;
+    int rc = p252_hash_tag(domain, in_len, out_len, &tag);
+    if (rc != P252_OK) return rc;
+    return digest_impl(ctx, &tag, in, n, in_len, out_raw, out_len, flags, true);
+}
+
+static int convert_impl(p252_ctx* ctx, const void* in, size_t n, void* out, uint8_t* ok, int flags, bool from_bytes) {
+    if (!ctx || ((!in || !out) && n)) return P252_ERR_INVALID_ARGUMENT;
+    DeviceGuard g(ctx->device);
+    if (flags & P252_MEM_DEVICE) {
+        if (!aligned16(in) || !aligned16(out)) return P252_ERR_INVALID_ARGUMENT;
+        if (n == 0) return P252_OK;
+        return finish_device_call(ctx, p252::launch_convert(in, n, out, ok, from_bytes, ctx->stream), flags);
+    }
+    std::vector<Io> ios = {{in, nullptr, 32}, {nullptr, out, 32}};
+    if (from_bytes && ok) ios.push_back({nullptr, ok, 1});
+    return run_host_pipeline(ctx, ios, n, [&](void** d, size_t cnt, cudaStream_t st) {
+        return p252::launch_convert(d[0], cnt, d[1], (from_bytes && ok) ? static_cast<uint8_t*>(d[2]) : nullptr, from_bytes, st);
+    });
+}
+
+int p252_scalars_from_bytes(p252_ctx* ctx, const uint8_t* bytes, size_t n, p252_fr* out, uint8_t* ok, int flags) {
+    return convert_impl(ctx, bytes, n, out, ok, flags, true);
+}
+
+int p252_scalars_to_bytes(p252_ctx* ctx, const p252_fr* in, size_t n, uint8_t* bytes, int flags) {
+    return convert_impl(ctx, in, n, bytes, nullptr, flags, false);
 }
 
 int p252_encrypt_batch(p252_ctx* ctx, const p252_fr* msg, size_t n, size_t L, const p252_fr* secret_uv,
@@ -531,7 +567,7 @@ static int merkle4_build_device(p252_ctx* ctx, const p252_fr* leaves, size_t n_l
     const p252_fr* src = leaves;
     p252_fr* dst = nodes;
     for (size_t m = n_leaves / 4; m >= 1; m /= 4) {
-        cudaError_t le = p252::launch_digest(limbs(&tag), src, m, 4, dst, 1, ctx->stream);
+        cudaError_t le = p252::launch_digest(limbs(&tag), src, m, 4, dst, 1, false, ctx->stream);
         if (le != cudaSuccess) return fail_cuda(ctx, le, "kernel launch");
         ctx->launches++;
         src = dst;
@@ -564,7 +600,7 @@ int p252_merkle4_build(p252_ctx* ctx, const p252_fr* leaves, size_t n_leaves, p2
         std::vector<Io> ios = {{leaves, nullptr, 128}, {nullptr, nodes_out, 32}};
         size_t done = 0;   // the pipeline hands chunks in order; mirror each chunk into d_nodes as well
         rc = run_host_pipeline(ctx, ios, n_leaves / 4, [&](void** d, size_t cnt, cudaStream_t st) {
-            cudaError_t e = p252::launch_digest(limbs(&tag), d[0], cnt, 4, d[1], 1, st);
+            cudaError_t e = p252::launch_digest(limbs(&tag), d[0], cnt, 4, d[1], 1, false, st);
             if (e != cudaSuccess) return e;
             e = cudaMemcpyAsync(d_nodes + done, d[1], cnt * sizeof(p252_fr), cudaMemcpyDeviceToDevice, st);
             done += cnt;
@@ -682,7 +718,7 @@ int p252_merkle4_build_dist(p252_ctx* ctx, const p252_fr* leaves_shard, size_t n
         p252_fr* level = nodes_out + p.level_offset;
         if (p.sharded) {
             // the first level is always sharded (n_leaves_total / G is a multiple of 4)
-            cudaError_t le = p252::launch_digest(limbs(&tag), below_mine, p.my_count, 4, level + p.my_offset, 1, ctx->stream);
+            cudaError_t le = p252::launch_digest(limbs(&tag), below_mine, p.my_count, 4, level + p.my_offset, 1, false, ctx->stream);
             if (le != cudaSuccess) return fail_cuda(ctx, le, "kernel launch");
             ctx->launches++;
             if (G > 1) {
@@ -698,7 +734,7 @@ int p252_merkle4_build_dist(p252_ctx* ctx, const p252_fr* leaves_shard, size_t n
                 CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_comm, 0));
                 gather_in_flight = false;
             }
-            cudaError_t le = p252::launch_digest(limbs(&tag), below_full, p.level_size, 4, level, 1, ctx->stream);
+            cudaError_t le = p252::launch_digest(limbs(&tag), below_full, p.level_size, 4, level, 1, false, ctx->stream);
             if (le != cudaSuccess) return fail_cuda(ctx, le, "kernel launch");
             ctx->launches++;
         }

@@ -191,6 +191,33 @@ __device__ __forceinline__ void fr_add_mod(uint32_t (&r)[8], const uint32_t (&a)
     fr_condsub(r);
 }
 
+// Montgomery form -> canonical integer in [0,p): x * 1 / R, one conditional subtraction (Scalar::reduce)
+__device__ __forceinline__ void fr_to_canonical(uint32_t (&r)[8], const uint32_t (&x)[8]) {
+    const uint32_t one[8] = {1, 0, 0, 0, 0, 0, 0, 0};
+    montmul(r, x, one);        // row operand x < p
+    fr_condsub(r);
+}
+
+// canonical integer (any 256-bit value) -> Montgomery form of (c mod p): c * R^2 / R
+__device__ __forceinline__ void fr_from_canonical(uint32_t (&r)[8], const uint32_t (&c)[8]) {
+    const uint32_t r2[8] = {0xf3f29c6du, 0xc999e990u, 0x87925c23u, 0x2b6cedcbu, 0x7254398fu, 0x05d31496u, 0x9f59ff11u,
+                            0x0748d9d9u};   // R^2 mod p
+    montmul(r, r2, c);         // row operand R^2 < p; c < 2^256  =>  result < 2p
+    fr_condsub(r);
+}
+
+// c < p ?  (borrow of c - p)
+__device__ __forceinline__ bool fr_is_canonical(const uint32_t (&c)[8]) {
+    uint32_t t[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) t[k] = c[k];
+    fr_condsub(t);             // t = c - p if c >= p else c   (valid for c < 2p; c >= 2p also changes t)
+    bool same = true;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) same = same && (t[k] == c[k]);
+    return same;
+}
+
 // ---------------------------------------------------------------------------------------------
 // Dense formulation: the reference's algorithm verbatim on the device (25 full products per MDS,
 // full reduction after every operation).  Cross-check / "what a straight port would cost".

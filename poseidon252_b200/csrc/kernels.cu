@@ -80,6 +80,10 @@ __device__ __forceinline__ void warp_scatter(uint4 (*st)[8], uint8_t* base, size
 // One permutation call site: step s > 0 is always preceded by a permutation; steps [0, nin) absorb
 // 4-scalar chunks, steps [nin, nin+nout) squeeze 4-scalar chunks.  Permutations = nin + nout - 1
 // = ceil(in_len/4) + ceil(out_len/4) - 1  (Merkle4: exactly 1).
+// kTruncate: Hash::finalize_truncated (/root/reference/src/hash.rs:164-183) -- every squeezed scalar is taken
+// out of Montgomery form and masked to 250 bits; the 4 x u64 written are the raw limbs the reference hands to
+// JubJubScalar::from_raw.
+template <bool kTruncate>
 __global__ void __launch_bounds__(kThreads, kMinBlocks) k_sponge_digest(FrArg tag, const uint8_t* __restrict__ in, size_t n,
                                                             uint32_t in_len, uint8_t* __restrict__ out,
                                                             uint32_t out_len) {
@@ -123,9 +127,15 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) k_sponge_digest(FrArg ta
             const int nscal = left < 4 ? (int)left : 4;
             uint32_t v[4][8];
 #pragma unroll
-            for (int q = 0; q < 4; ++q)
+            for (int q = 0; q < 4; ++q) {
+                if (kTruncate) {
+                    fr_to_canonical(v[q], s[1 + q]);
+                    v[q][7] &= 0x03ffffffu;               // TRUNCATION_MASK, src/hash.rs:167-172
+                } else {
 #pragma unroll
-                for (int k = 0; k < 8; ++k) v[q][k] = s[1 + q][k];
+                    for (int k = 0; k < 8; ++k) v[q][k] = s[1 + q][k];
+                }
+            }
             warp_scatter(st, out_w + (size_t)c * 128, (size_t)out_len * 32, nitems, nscal, lane, v);
         }
     }
@@ -293,10 +303,48 @@ cudaError_t launch_permute(void* states, size_t n, bool dense, cudaStream_t st) 
 }
 
 cudaError_t launch_digest(const uint64_t tag[4], const void* in, size_t n, uint32_t in_len, void* out,
-                          uint32_t out_len, cudaStream_t st) {
+                          uint32_t out_len, bool truncate, cudaStream_t st) {
     if (n == 0) return cudaSuccess;
-    k_sponge_digest<<<grid_for(n), kThreads, 0, st>>>(to_arg(tag), static_cast<const uint8_t*>(in), n, in_len,
-                                                      static_cast<uint8_t*>(out), out_len);
+    if (truncate)
+        k_sponge_digest<true><<<grid_for(n), kThreads, 0, st>>>(to_arg(tag), static_cast<const uint8_t*>(in), n, in_len,
+                                                                static_cast<uint8_t*>(out), out_len);
+    else
+        k_sponge_digest<false><<<grid_for(n), kThreads, 0, st>>>(to_arg(tag), static_cast<const uint8_t*>(in), n, in_len,
+                                                                 static_cast<uint8_t*>(out), out_len);
+    return cudaGetLastError();
+}
+
+// ---- wire format: canonical 32-byte little-endian <-> BlsScalar.0 (Montgomery limbs) ---------------------
+// BlsScalar::from_bytes / to_bytes (used at /root/reference/src/hades.rs:94-105,131 and
+// src/hades/round_constants.rs:64-68).  Elementwise, 32 B in + 32 B out per scalar: the one HBM-bound kernel.
+template <bool kFromBytes>
+__global__ void __launch_bounds__(256) k_convert(const uint8_t* __restrict__ in, size_t n, uint8_t* __restrict__ out,
+                                                 uint8_t* __restrict__ ok) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint32_t x[8], r[8];
+    load_fr(x, in + i * 32);
+    if (kFromBytes) {
+        const bool valid = fr_is_canonical(x);               // from_bytes rejects values >= p
+        fr_from_canonical(r, x);
+        if (!valid) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) r[k] = 0;
+        }
+        if (ok) ok[i] = valid ? 1 : 0;
+    } else {
+        fr_to_canonical(r, x);
+    }
+    store_fr(out + i * 32, r);
+}
+
+cudaError_t launch_convert(const void* in, size_t n, void* out, uint8_t* ok, bool from_bytes, cudaStream_t st) {
+    if (n == 0) return cudaSuccess;
+    const unsigned grid = (unsigned)((n + 255) / 256);
+    if (from_bytes)
+        k_convert<true><<<grid, 256, 0, st>>>(static_cast<const uint8_t*>(in), n, static_cast<uint8_t*>(out), ok);
+    else
+        k_convert<false><<<grid, 256, 0, st>>>(static_cast<const uint8_t*>(in), n, static_cast<uint8_t*>(out), nullptr);
     return cudaGetLastError();
 }
 

@@ -10,7 +10,8 @@ namespace p252 {
 
 cudaError_t launch_permute(void* states, size_t n, bool dense, cudaStream_t st);
 cudaError_t launch_digest(const uint64_t tag[4], const void* in, size_t n, uint32_t in_len, void* out,
-                          uint32_t out_len, cudaStream_t st);
+                          uint32_t out_len, bool truncate, cudaStream_t st);
+cudaError_t launch_convert(const void* in, size_t n, void* out, uint8_t* ok, bool from_bytes, cudaStream_t st);
 cudaError_t launch_encrypt(const uint64_t tag[4], const void* msg, size_t n, uint32_t L, const void* secret_uv,
                            const void* nonce, void* cipher, cudaStream_t st);
 cudaError_t launch_decrypt(const uint64_t tag[4], const void* cipher, size_t n, uint32_t L, const void* secret_uv,

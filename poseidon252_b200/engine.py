@@ -150,6 +150,49 @@ class Engine:
                                               flags | (_native.ASYNC if async_ and flags else 0)))
         return res
 
+    def hash_batch_truncated(self, domain, inputs, out_len=1, out=None, async_=False):
+        """n x Hash::digest_truncated: raw (canonical, 250-bit masked) limbs for JubJubScalar::from_raw."""
+        if inputs.ndim != 3:
+            raise EngineError(-1, "inputs must have shape (n, in_len, 4)")
+        in_len = int(inputs.shape[1])
+        ptr, lead, flags, keep = self._in(inputs, (in_len, 4))
+        n = lead[0]
+        res = self._out_like(keep, (n, int(out_len), 4)) if out is None else out
+        self._check(self._lib.p252_hash_batch_truncated(self._ctx, int(domain), ptr, n, in_len, self._ptr(res),
+                                                        int(out_len), flags | (_native.ASYNC if async_ and flags else 0)))
+        return res
+
+    def scalars_from_bytes(self, data, async_=False):
+        """(n, 32) uint8 canonical little-endian (host) or (n, 4) 64-bit device tensor of the same bytes
+        -> (scalars (n, 4), ok (n,) uint8); ok == 0 where the value is >= p."""
+        if _is_torch(data):
+            import torch
+            ptr, lead, flags, keep = self._in(data, (4,))
+            n = lead[0]
+            out = torch.empty((n, 4), dtype=keep.dtype, device=keep.device)
+            ok = torch.empty((n,), dtype=torch.uint8, device=keep.device)
+        else:
+            keep = np.ascontiguousarray(data, dtype=np.uint8).reshape(-1, 32)
+            ptr, n, flags = keep.ctypes.data, keep.shape[0], _native.MEM_HOST
+            out = np.empty((n, 4), dtype=np.uint64)
+            ok = np.empty((n,), dtype=np.uint8)
+        self._check(self._lib.p252_scalars_from_bytes(self._ctx, ptr, n, self._ptr(out), self._ptr(ok),
+                                                      flags | (_native.ASYNC if async_ and flags else 0)))
+        return out, ok
+
+    def scalars_to_bytes(self, scalars, async_=False):
+        """(n, 4) scalars -> canonical little-endian bytes: (n, 32) uint8 (host) or (n, 4) device tensor."""
+        ptr, lead, flags, keep = self._in(scalars, (4,))
+        n = lead[0]
+        if _is_torch(keep):
+            import torch
+            out = torch.empty((n, 4), dtype=keep.dtype, device=keep.device)
+        else:
+            out = np.empty((n, 32), dtype=np.uint8)
+        self._check(self._lib.p252_scalars_to_bytes(self._ctx, ptr, n, self._ptr(out),
+                                                    flags | (_native.ASYNC if async_ and flags else 0)))
+        return out
+
     def encrypt_batch(self, messages, secrets_uv, nonces, out=None, async_=False):
         """messages (n, L, 4), secrets_uv (n, 2, 4), nonces (n, 4) -> ciphers (n, L+1, 4)."""
         L = int(messages.shape[1])

@@ -100,10 +100,17 @@ class Hash:
         return out[0]
 
     def finalize_truncated(self):
-        """src/hash.rs:164-183: canonical value & (2^250 - 1) as JubJubScalar limbs (non-Montgomery
-        raw limbs handed to JubJubScalar::from_raw -> returned here as canonical integers)."""
-        mask = (1 << 250) - 1
-        return [int(v) & mask for v in from_mont(self.finalize())]
+        """src/hash.rs:164-183: canonical value & (2^250 - 1); returns the (out_len, 4) raw u64 limbs that the
+        reference hands to JubJubScalar::from_raw (computed on the device, see digest_truncated_batch)."""
+        lens = [int(c.shape[0]) for c in self.input]
+        if len(lens) != 1:
+            # chunked updates only change the tag; use the generic path + host post-step
+            mask = (1 << 250) - 1
+            vals = [int(v) & mask for v in from_mont(self.finalize())]
+            return np.array([[(v >> (64 * k)) & ((1 << 64) - 1) for k in range(4)] for v in vals], dtype=np.uint64)
+        io_pattern(self.domain, lens, self._output_len)
+        eng = self._engine or default_engine()
+        return eng.hash_batch_truncated(self.domain, self.input[0].reshape(1, -1, 4), self._output_len)[0]
 
     @staticmethod
     def digest(domain, data, engine=None):
@@ -118,6 +125,14 @@ class Hash:
         h = Hash(domain, engine)
         h.update(data)
         return h.finalize_truncated()
+
+    @staticmethod
+    def digest_truncated_batch(domain, inputs, output_len=1, engine=None, out=None, async_=False):
+        """NEW batch entry: n x Hash::digest_truncated -> (n, out_len, 4) raw limbs (< 2^250)."""
+        domain = Domain(domain)
+        ol = int(output_len) if (domain == Domain.Other and output_len > 0) else 1
+        eng = engine or default_engine(inputs.device.index if hasattr(inputs, "is_cuda") else 0)
+        return eng.hash_batch_truncated(domain, inputs, ol, out=out, async_=async_)
 
     @staticmethod
     def digest_batch(domain, inputs, output_len=1, engine=None, out=None, async_=False):

@@ -23,7 +23,7 @@ def header_symbols():
 def test_library_exports_every_declared_symbol():
     lib = _native.lib()
     names = header_symbols()
-    assert len(names) >= 25
+    assert len(names) >= 30
     for n in names:
         assert hasattr(lib, n), n
     assert sorted(_native.SIGNATURES) == names

@@ -251,3 +251,62 @@ def test_full_size_encrypt_roundtrip(engine):
     non2[::2, 0] ^= np.uint64(1)
     _, ok2 = pb.decrypt_batch(c, sec, non2, engine=engine)
     assert not ok2[::2].any() and ok2[1::2].all()
+
+
+# ---- "next" rows of SURVEY 8(f): truncated digests and the wire format ------------------------------------
+def test_digest_truncated(engine, oracle):
+    """Hash::digest_truncated / finalize_truncated, src/hash.rs:164-183,203-210 (shapes of tests/hash.rs:188-203)."""
+    rng = np.random.default_rng(31)
+    for in_len, out_len in ((3, 1), (5, 1), (15, 1), (4, 7)):
+        data = random_scalars(rng, (50, in_len))
+        got = pb.Hash.digest_truncated_batch(pb.Domain.Other, data, out_len, engine=engine)
+        assert got.shape == (50, out_len, 4)
+        for i in (0, 17, 49):
+            h = oracle.Hash(oracle.Domain.Other)
+            h.output_len(out_len)
+            h.update([int(v) for v in unmont(data[i])])
+            want = h.finalize_truncated()
+            have = [sum(int(got[i, o, k]) << (64 * k) for k in range(4)) for o in range(out_len)]
+            assert have == want and all(v < (1 << 250) for v in have)
+    # single-item API and the Merkle4 domain
+    x = random_scalars(rng, 4)
+    one = pb.Hash.digest_truncated(pb.Domain.Merkle4, x, engine)
+    want = oracle.Hash.digest_truncated(oracle.Domain.Merkle4, [int(v) for v in unmont(x)])
+    assert [sum(int(one[0, k]) << (64 * k) for k in range(4))] == want
+    h = pb.Hash(pb.Domain.Other, engine)
+    h.update(x[:1])
+    h.update(x[1:])
+    want = oracle.Hash.digest_truncated(oracle.Domain.Other, [int(v) for v in unmont(x)])
+    assert [sum(int(h.finalize_truncated()[0, k]) << (64 * k) for k in range(4))] == want
+
+
+def test_wire_format_roundtrip(engine, oracle):
+    """BlsScalar::from_bytes / to_bytes (src/hades.rs:94-105 parses its KAT inputs this way;
+    src/hades/round_constants.rs:64-68 round-trips every constant)."""
+    kin = oracle.kat_inputs()
+    raw = np.frombuffer(b"".join(bytes.fromhex(s) for s in oracle.KAT_INPUTS_LE_HEX), dtype=np.uint8).reshape(-1, 32)
+    sc, ok = engine.scalars_from_bytes(raw)
+    assert ok.all() and [int(v) for v in unmont(sc)] == kin
+    assert np.array_equal(engine.scalars_to_bytes(sc), raw)
+    # all 340 round constants round-trip
+    arc = mont(oracle._ARC_FLAT)
+    b = engine.scalars_to_bytes(arc)
+    assert b.tobytes() == oracle.arc_bin_bytes()
+    back, ok = engine.scalars_from_bytes(b)
+    assert ok.all() and np.array_equal(back, arc)
+    # non-canonical encodings are rejected like from_bytes -> None
+    bad = np.stack([np.frombuffer(v.to_bytes(32, "little"), dtype=np.uint8)
+                    for v in (oracle.P, oracle.P + 1, (1 << 256) - 1, oracle.P - 1, 0)])
+    sc, ok = engine.scalars_from_bytes(bad)
+    assert list(ok) == [0, 0, 0, 1, 1] and not sc[:3].any()
+    assert [int(v) for v in unmont(sc[3:])] == [oracle.P - 1, 0]
+    # large ragged batch, device tensors
+    import torch
+    rng = np.random.default_rng(32)
+    big = random_scalars(rng, 100003 // 100)          # ~1000 scalars
+    d = torch.from_numpy(big.view(np.int64)).cuda()
+    db = engine.scalars_to_bytes(d)
+    dback, dok = engine.scalars_from_bytes(db)
+    assert bool(dok.all()) and np.array_equal(dback.cpu().numpy().view(np.uint64), big)
+    assert [int.from_bytes(r.tobytes(), "little") for r in db.cpu().numpy().view(np.uint8).reshape(-1, 32)[:5]] == \
+        [int(v) for v in unmont(big[:5])]
