@@ -185,8 +185,9 @@ def main():
     ap.add_argument("--steps", type=int, default=40)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="merkle4", choices=["merkle4", "encrypt", "permute", "sweep", "tree"])
+    ap.add_argument("--workload", default="merkle4", choices=["merkle4", "encrypt", "permute", "sweep", "tree", "convert"])
     ap.add_argument("--log2-batch", type=int, default=LOG2_BATCH)
+    ap.add_argument("--log4-leaves", type=int, default=0, help="tree workload: 4^k leaves in the whole job (14 = BASELINE configs[3])")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
@@ -269,8 +270,17 @@ def main():
                 pb.Hash.digest_batch(pb.Domain.Other, bufs[L], engine=eng, out=out, async_=True)
         workload = "sponge sweep Domain::Other, in_len in %s, batch 2^18 per length" % lens
         l2_note = "each length's input is its own buffer; total %d MiB per step" % (bytes_per_step >> 20)
+    elif args.workload == "convert":
+        n = 1 << 25                                       # 1 GiB of scalars in, 1 GiB of bytes out
+        with torch.cuda.stream(stream):
+            sc = torch.from_numpy(random_limbs_fast(rng, (n,)).view(np.int64)).cuda()
+            ob = torch.empty((n, 4), dtype=torch.int64, device="cuda")
+        perms_per_step, bytes_per_step = n, n * 64       # "perms" here = scalars converted (no permutation)
+        lib, ctx = eng._lib, eng._ctx
+        step = lambda i: eng._check(lib.p252_scalars_to_bytes(ctx, sc.data_ptr(), n, ob.data_ptr(), 3))
+        workload, l2_note = "to_bytes of 2^25 scalars (wire-format kernel, the one HBM-bound kernel); value = scalars/s", "1 GiB in + 1 GiB out per step"
     else:  # tree
-        k = 11 if world == 1 else 12
+        k = args.log4_leaves or (11 if world == 1 else 12)
         n_leaves = 4 ** k
         shard = n_leaves // world
         uid = eng.dist_unique_id() if rank == 0 else bytes(128)
@@ -354,7 +364,8 @@ def main():
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": ncu_traffic(), "peak_source": peak_src,
                 "kernel": "k_sponge_digest" if args.workload in ("merkle4", "sweep", "tree") else
-                          ("k_crypt<false>" if args.workload == "encrypt" else "k_permute<false>"),
+                          ("k_crypt<false>" if args.workload == "encrypt" else
+                           ("k_convert<false>" if args.workload == "convert" else "k_permute<false>")),
                 "algorithmic_bytes_per_launch": bytes_per_step // max(1, launches // args.steps),
                 "launch_ms": launch_ms,
                 "note": "the path is integer-issue bound (~10^3 integer ops per byte), not HBM bound; see int_pipe",
