@@ -372,7 +372,8 @@ def main():
                 "int_pipe": {"perm_per_s_per_sm_clock": value / world / sm_clock,
                              "note": "profiles/ holds the ncu fma/alu pipe utilisation of this kernel"}}
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "ms_per_step": total_ms / args.steps, "higher_is_better": True,
+            "scaling": "strong" if args.workload == "tree" else "weak", "vs_baseline": None,
             "dtype": "u32 limbs (255-bit modular integer, IMAD.WIDE carry chains)", "data": "synthetic",
             "config": {"workload": workload, "per_gpu_batch": perms_per_step, "l2": l2_note, "parallelism": "dp%d, no collective on the data path" % world
                        if args.workload != "tree" else "leaf shards, NCCL all-gather per level"},
