@@ -109,13 +109,18 @@ def measured_peaks():
         return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
-def ncu_traffic():
-    """dram bytes per launch of the dominant kernel from the committed ncu summary, if present."""
+def ncu_summary():
+    """The committed ncu summary of the dominant kernel (profiles/r1_ncu_summary.json), if present."""
     try:
         with open(os.path.join(ROOT, "profiles", "r1_ncu_summary.json")) as f:
-            return json.load(f).get("merkle4_2p20", {}).get("dram_bytes_per_launch")
+            return json.load(f).get("merkle4_2p20", {})
     except Exception:
-        return None
+        return {}
+
+
+def ncu_traffic():
+    """dram bytes per launch of the dominant kernel from the committed ncu capture."""
+    return ncu_summary().get("dram_bytes_per_launch")
 
 
 # ---------------------------------------------------------------------------------------------------------
@@ -370,7 +375,10 @@ def main():
                 "launch_ms": launch_ms,
                 "note": "the path is integer-issue bound (~10^3 integer ops per byte), not HBM bound; see int_pipe",
                 "int_pipe": {"perm_per_s_per_sm_clock": value / world / sm_clock,
-                             "note": "profiles/ holds the ncu fma/alu pipe utilisation of this kernel"}}
+                             "ncu_pipe_fmaheavy_active_pct": ncu_summary().get("pipe_fmaheavy_active_pct"),
+                             "ncu_issue_active_pct": ncu_summary().get("issue_active_pct"),
+                             "ncu_imad_wide_per_permutation": (ncu_summary().get("warp_instructions_per_warp") or {}).get("IMAD.WIDE"),
+                             "note": "from the committed ncu capture in profiles/ (the limiting resource is the IMAD pipe)"}}
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": total_ms / args.steps, "higher_is_better": True,
             "scaling": "strong" if args.workload == "tree" else "weak", "vs_baseline": None,
