@@ -191,10 +191,13 @@ __device__ __forceinline__ void fr_add_mod(uint32_t (&r)[8], const uint32_t (&a)
     fr_condsub(r);
 }
 
-// Montgomery form -> canonical integer in [0,p): x * 1 / R, one conditional subtraction (Scalar::reduce)
+// Montgomery form -> canonical integer in [0,p): x / R, i.e. the eight reduction rows alone applied to (x, 0)
+// (no product needed), then one conditional subtraction (Scalar::reduce)
 __device__ __forceinline__ void fr_to_canonical(uint32_t (&r)[8], const uint32_t (&x)[8]) {
-    const uint32_t one[8] = {1, 0, 0, 0, 0, 0, 0, 0};
-    montmul(r, x, one);        // row operand x < p
+    uint32_t t[16];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) t[k] = x[k], t[8 + k] = 0;
+    fr_redc_wide(r, t);        // (x + m p) / 2^256 < p + 1
     fr_condsub(r);
 }
 
