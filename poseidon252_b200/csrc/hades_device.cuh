@@ -19,9 +19,51 @@
 
 #include "fr_ptx.cuh"
 
+#ifndef P252_CONST_SMEM
+#define P252_CONST_SMEM 0     // 1: round tables staged into shared memory with one TMA bulk copy per block
+#endif
+
 namespace p252 {
 
 #include "hades_tables.inc"
+
+#if P252_CONST_SMEM
+// Experiment (north_star's suggestion): stage kA|kG into shared memory once per block with cp.async.bulk
+// (TMA, completion on an mbarrier) and read them with broadcast LDS instead of LDCU from the constant bank.
+__device__ __forceinline__ const uint32_t* stage_round_tables(uint32_t* s_tab, uint64_t* mbar) {
+    const uint32_t bar = (uint32_t)__cvta_generic_to_shared(mbar);
+    const uint32_t dst = (uint32_t)__cvta_generic_to_shared(s_tab);
+    constexpr uint32_t kBytes = P252_TAB_WORDS * 4;
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(kBytes) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                     "l"(gRoundTab), "r"(kBytes), "r"(bar)
+                     : "memory");
+    }
+    uint32_t done = 0;
+    while (!done) {
+        asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0; selp.u32 %0, 1, 0, p; }"
+                     : "=r"(done)
+                     : "r"(bar)
+                     : "memory");
+    }
+    return s_tab;
+}
+#define P252_TAB_ARG , const uint32_t* tab
+#define P252_TAB_PASS , tab
+#define P252_A_ROW(round, lane) (tab + ((round) * 5 + (lane)) * 12)
+#define P252_G_ROW(idx) (tab + P252_TAB_A_WORDS + (idx) * 8)
+#else
+#define P252_TAB_ARG
+#define P252_TAB_PASS
+#define P252_A_ROW(round, lane) (kA[round][lane])
+#define P252_G_ROW(idx) (kG[idx])
+#endif
 
 // hades_tables.inc defines, in the constant bank (statically initialised at module load):
 //   kA0[5][8], kA[69][5][12]  per-round additive constants (scaled)   kG[60][8]  lane-4 correction
@@ -95,7 +137,7 @@ constexpr double kTwo52 = 4503599627370496.0;
 // into the 9-limb totals t[i] (column k overlaps column k+1 by its upper word).  The exponent words are not
 // masked off: their sum K_off is pre-subtracted (mod 2^288) from the 9-limb round constant kA[next_round][i],
 // and the addition inside fr_arc_redc1 wraps to the true integer C s + A < 2^288.
-__device__ __forceinline__ void mix(uint32_t (&s)[5][8], int next_round) {
+__device__ __forceinline__ void mix(uint32_t (&s)[5][8], int next_round P252_TAB_ARG) {
     uint32_t t[5][9];
     uint32_t hi_prev[5] = {0, 0, 0, 0, 0}, carry[5] = {0, 0, 0, 0, 0};
 #pragma unroll
@@ -119,13 +161,13 @@ __device__ __forceinline__ void mix(uint32_t (&s)[5][8], int next_round) {
         t[i][8] = hi_prev[i] + carry[i];
         uint32_t c[9];
 #pragma unroll
-        for (int k = 0; k < 9; ++k) c[k] = kA[next_round][i][k];
+        for (int k = 0; k < 9; ++k) c[k] = P252_A_ROW(next_round, i)[k];
         fr_arc_redc1(s[i], t[i], c);
     }
 }
 
 // In-register Hades permutation, standard Montgomery form in and out (both < p).
-__device__ __forceinline__ void hades_permute(uint32_t (&s)[5][8]) {
+__device__ __forceinline__ void hades_permute(uint32_t (&s)[5][8] P252_TAB_ARG) {
     uint32_t c[8];
     // first add_round_constants: explicit, then one full conditional subtraction
 #pragma unroll
@@ -157,11 +199,11 @@ __device__ __forceinline__ void hades_permute(uint32_t (&s)[5][8]) {
                     s[0][k] = w[k];
                 }
             } else {
-                load_const(c, kG[r - kHalfFull]);
+                load_const(c, P252_G_ROW(r - kHalfFull));
                 montmul(s[4], c, w);
             }
         }
-        mix(s, r + 1);      // r + 1 == kRounds: row 68 of kA carries no round constants
+        mix(s, r + 1 P252_TAB_PASS);      // r + 1 == kRounds: row 68 of kA carries no round constants
     }
     // leave the scaled domain: out = montmul(F, v) fully reduced
     load_const(c, kF);

@@ -25,6 +25,15 @@ constexpr int kThreads = P252_THREADS;
 constexpr int kMinBlocks = P252_MINBLOCKS;
 constexpr int kWarps = kThreads / 32;
 
+#if P252_CONST_SMEM
+#define P252_STAGE_TABLES                                             \
+    __shared__ __align__(128) uint32_t s_round_tab[P252_TAB_WORDS];   \
+    __shared__ __align__(8) uint64_t s_tab_bar;                       \
+    const uint32_t* tab = stage_round_tables(s_round_tab, &s_tab_bar);
+#else
+#define P252_STAGE_TABLES
+#endif
+
 struct FrArg {
     uint32_t l[8];
 };
@@ -88,6 +97,7 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) k_sponge_digest(FrArg ta
                                                             uint32_t in_len, uint8_t* __restrict__ out,
                                                             uint32_t out_len) {
     __shared__ uint4 stage[kWarps][32][8];
+    P252_STAGE_TABLES
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
     const size_t item0 = ((size_t)blockIdx.x * kWarps + warp) * 32;
@@ -106,7 +116,7 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) k_sponge_digest(FrArg ta
     uint8_t* out_w = out + item0 * (size_t)out_len * 32;
 #pragma unroll 1
     for (uint32_t step = 0; step < nin + nout; ++step) {
-        if (step > 0) hades_permute(s);
+        if (step > 0) hades_permute(s P252_TAB_PASS);
         if (step < nin) {
             const uint32_t left = in_len - 4 * step;
             const int nscal = left < 4 ? (int)left : 4;
@@ -145,6 +155,7 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) k_sponge_digest(FrArg ta
 template <bool kDense>
 __global__ void __launch_bounds__(kThreads, kDense ? 1 : kMinBlocks) k_permute(uint8_t* __restrict__ states, size_t n) {
     __shared__ uint4 stage[kWarps][32][8];
+    P252_STAGE_TABLES
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
     const size_t item0 = ((size_t)blockIdx.x * kWarps + warp) * 32;
@@ -168,7 +179,7 @@ __global__ void __launch_bounds__(kThreads, kDense ? 1 : kMinBlocks) k_permute(u
     if (kDense)
         dense_permute(s);
     else
-        hades_permute(s);
+        hades_permute(s P252_TAB_PASS);
     {
         uint32_t v[4][8];
 #pragma unroll
@@ -204,6 +215,7 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) k_crypt(FrArg tag, const
                                                     const uint8_t* __restrict__ secret_uv,
                                                     const uint8_t* __restrict__ nonce, uint8_t* dst,
                                                     uint8_t* __restrict__ ok) {
+    P252_STAGE_TABLES
     const size_t i = (size_t)blockIdx.x * kThreads + threadIdx.x;
     if (i >= n) return;
     // encrypt: src = message (n x L), dst = cipher (n x (L+1)); decrypt: the other way round
@@ -222,7 +234,7 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) k_crypt(FrArg tag, const
     bool good = true;
 #pragma unroll 1
     for (uint32_t step = 0; step < 2 * nk; ++step) {
-        hades_permute(s);
+        hades_permute(s P252_TAB_PASS);
         if (step < nk) {
             // Squeeze chunk `step` of the keystream and emit cipher (or recovered message)
             const uint32_t left = L - 4 * step;
