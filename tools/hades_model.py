@@ -211,19 +211,29 @@ def limbs32(v: int, n: int = 8) -> List[int]:
     return [(v >> (32 * i)) & M32 for i in range(n)]
 
 
+def permute_dense(state_mont: Sequence[int]) -> List[int]:
+    """The reference's dense formulation on canonical integers (src/hades/permutation.rs:105-123 with
+    scalar.rs:39-64), used only to self-check the scaled-lazy model inside this build tool."""
+    s = [x * R_INV % P for x in state_mont]
+    for r in range(ROUNDS):
+        s = [(x + ARC[r * WIDTH + i]) % P for i, x in enumerate(s)]
+        if is_full(r):
+            s = [pow(x, 5, P) for x in s]
+        else:
+            s[4] = pow(s[4], 5, P)
+        s = [sum(MDS[i][j] * s[j] for j in range(WIDTH)) % P for i in range(WIDTH)]
+    return [x * R % P for x in s]
+
+
 if __name__ == "__main__":
     import random
-    import sys
-    sys.path.insert(0, __import__("os").path.join(__import__("os").path.dirname(__file__), "..", "oracle"))
-    import hades_oracle as o          # model self-check only (tools/ is not the product path)
 
     rnd = random.Random(7)
     cases = [[0] * 5, [1] * 5, [P - 1] * 5, [17] * 5, list(range(5))]
-    cases += [[rnd.randrange(P) for _ in range(5)] for _ in range(200)]
+    cases += [[rnd.randrange(P) for _ in range(5)] for _ in range(100)]
     for c in cases:
-        got = permute_model([x * R % P for x in c])
-        want = [x * R % P for x in o.perm(c)]
-        assert got == want, c
-    print("scaled-lazy model == oracle on", len(cases), "states")
+        m = [x * R % P for x in c]
+        assert permute_model(m) == permute_dense(m), c
+    print("scaled-lazy model == dense formulation on", len(cases), "states")
     for k, v in sorted(Bounds.seen.items()):
         print("  max %-8s %.5f p   (2^256 = %.5f p)" % (k, v, TWO256 / P))
