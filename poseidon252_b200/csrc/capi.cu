@@ -130,8 +130,10 @@ struct Io {
     size_t item_bytes;   // bytes per batch item
 };
 
+// wipe = true: the staging arenas held secrets (shared secret, nonce, plaintext); clear them before returning
+// (the reference's dependencies zeroize sponge state, Cargo.toml:15,17 "zeroize").
 template <typename Launch>
-int run_host_pipeline(p252_ctx* ctx, std::vector<Io>& ios, size_t n, Launch launch) {
+int run_host_pipeline(p252_ctx* ctx, std::vector<Io>& ios, size_t n, Launch launch, bool wipe = false) {
     if (n == 0) return P252_OK;
     size_t per_item = 0;
     for (auto& io : ios) per_item += (io.item_bytes + 15) / 16 * 16;
@@ -175,6 +177,8 @@ int run_host_pipeline(p252_ctx* ctx, std::vector<Io>& ios, size_t n, Launch laun
     }
     // join: the context stream continues after every slot
     for (int s = 0; s < kSlots; ++s) {
+        if (wipe && ctx->slots[s].arena)
+            CU(cudaMemsetAsync(ctx->slots[s].arena, 0, ctx->slots[s].arena_bytes, ctx->slots[s].stream));
         CU(cudaEventRecord(ctx->ev_join[s], ctx->slots[s].stream));
         CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_join[s], 0));
     }
@@ -508,7 +512,7 @@ int p252_encrypt_batch(p252_ctx* ctx, const p252_fr* msg, size_t n, size_t L, co
                            {nullptr, cipher, (L + 1) * 32}};
     return run_host_pipeline(ctx, ios, n, [&](void** d, size_t cnt, cudaStream_t st) {
         return p252::launch_encrypt(limbs(&tag), d[0], cnt, l32, d[1], d[2], d[3], st);
-    });
+    }, /*wipe=*/true);
 }
 
 int p252_decrypt_batch(p252_ctx* ctx, const p252_fr* cipher, size_t n, size_t L, const p252_fr* secret_uv,
@@ -531,7 +535,7 @@ int p252_decrypt_batch(p252_ctx* ctx, const p252_fr* cipher, size_t n, size_t L,
                            {nullptr, msg, L * 32}, {nullptr, ok, 1}};
     rc = run_host_pipeline(ctx, ios, n, [&](void** d, size_t cnt, cudaStream_t st) {
         return p252::launch_decrypt(limbs(&tag), d[0], cnt, l32, d[1], d[2], d[3], static_cast<uint8_t*>(d[4]), st);
-    });
+    }, /*wipe=*/true);
     if (rc == P252_OK && n_failed) {
         size_t bad = 0;
         for (size_t i = 0; i < n; ++i) bad += ok[i] ? 0 : 1;
