@@ -11,8 +11,8 @@
 //   * the MDS layer is 25 small-integer (<= 17 bit) multiply-adds per round, computed EXACTLY in FP64
 //     (DFMA on the otherwise idle FP64 pipe; column sums < 2^52) followed by ONE Montgomery row per
 //     lane; round constants ride inside that same accumulation;
-//   * values stay in [0, 2^256) without modular correction except one predicated subtraction per
-//     S-box (bound analysis: DESIGN.md "Operand bounds").
+//   * values stay in [0, 2^256) with no modular correction at all between the first round's add and the
+//     final output (bound analysis: DESIGN.md "Operand bounds"; asserted by the emulator and the model).
 // Input and output are BlsScalar.0 (4 x u64 LE limbs, Montgomery form, < p), bit-exact.
 #pragma once
 #include <stdint.h>
@@ -111,16 +111,6 @@ __device__ __forceinline__ void load_const(uint32_t (&d)[8], const uint32_t* c) 
     for (int k = 0; k < 8; ++k) d[k] = c[k];
 }
 
-// One lane of the MDS layer: t = sum_j C[i][j] * z[j].
-//
-// The 25 products per round are (<= 17 bit constant) x (32-bit limb); a column sum over the five lanes is
-// below 268697 * 2^32 < 2^50.1, i.e. EXACT in an IEEE double.  B200 has a full-rate FP64 pipe that the
-// integer kernel leaves idle, so the column sums are formed with DFMA on that pipe (concurrently with the
-// IMAD.WIDE carry chains of the S-box on the fmaheavy pipe) instead of 40 IMAD.WIDE per lane:
-//   limb -> double : bit-pattern trick, (2^52 | limb) - 2^52 (one DADD, exact)
-//   acc = 2^52 + sum_j c_ij * limb_j  (five DFMA, every partial sum is an integer < 2^53: no rounding)
-//   column = mantissa bits of acc (low word | 20 bits of the high word).
-// zd[j][k] holds limb k of lane j as a double.
 constexpr double kTwo52 = 4503599627370496.0;
 
 // s <- redc1(C s + A[next_round]) in place -- mul_matrix (+ the next add_round_constants) of the reference,
