@@ -86,3 +86,25 @@ def test_no_cpu_fallback_without_gpu():
         pb.Engine(0)
     with pytest.raises(pb.EngineError):
         pb.Hash.digest(pb.Domain.Merkle4, pb.scalar.to_mont([1, 2, 3, 4]))
+
+
+def test_tag_input_random_patterns_match_oracle(oracle):
+    """Random valid io-patterns (absorb first, squeeze last, arbitrary alternation and repeats): the library's
+    aggregation + big-endian encoding equals the oracle's restatement of dusk-safe's tag input."""
+    import random
+    rnd = random.Random(2024)
+    for _ in range(300):
+        n = rnd.randrange(2, 9)
+        kinds = ["absorb"] + [rnd.choice(["absorb", "squeeze"]) for _ in range(n - 2)] + ["squeeze"]
+        pat = [(k, rnd.randrange(1, 1 << rnd.randrange(1, 20))) for k in kinds]
+        dsep = rnd.choice([0, 0xF, 0x3, 1 << 32, rnd.randrange(1 << 64)])
+        assert H.tag_input(pat, dsep) == oracle.tag_input(pat, dsep)
+        assert pb.scalar.from_mont(H.tag(pat, dsep)) == oracle.hash_to_scalar(oracle.tag_input(pat, dsep))
+    # invalid patterns are rejected like dusk-safe's validation
+    lib = _native.lib()
+    buf = (ctypes.c_uint8 * 64)()
+    n = ctypes.c_size_t(64)
+    for calls in ([5], [0x80000005], [5, 0x80000001], [0x80000000, 1], [0x80000003, 0]):
+        arr = np.array(calls, dtype=np.uint32)
+        n.value = 64
+        assert lib.p252_tag_input(arr.ctypes.data, len(calls), 0, buf, ctypes.byref(n)) == 2   # InvalidIOPattern
