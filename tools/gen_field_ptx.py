@@ -69,6 +69,7 @@ class Prog:
     def run(self, env: Dict[str, int]) -> Dict[str, int]:
         reg = dict(env)
         cf = 0
+        cf_kind = None          # "add" or "sub": which flavour produced the live carry flag
         preds: Dict[str, bool] = {}
 
         def val(x):
@@ -102,6 +103,13 @@ class Prog:
             uses_c = base.endswith("c") and base in ("madc", "addc", "subc")
             sets_cc = opc.endswith(".cc.u32") or ".cc" in opc
             cin = cf if uses_c else 0
+            kind = "sub" if base in ("sub", "subc") else "add"
+            if uses_c:
+                # On the GPU a borrow written by sub.cc is NOT a carry for addc/madc (and vice versa) even though
+                # PTX names one flag: measured on B200 (rejected experiments).  Never mix flavours.
+                assert cf_kind == kind, "carry chain mixes add and sub flavours in %s at %s" % (self.name, opc)
+            if sets_cc:
+                cf_kind = kind
             if base in ("mul",):
                 prod = val(src[0]) * val(src[1])
                 full = (prod & M32) if ".lo" in opc else (prod >> 32)
