@@ -45,10 +45,14 @@ def main():
     hdr, units, vals = rows[0], rows[1], rows[2]
     res = {"kernel": vals[hdr.index("Kernel Name")].split("(")[0], "grid": vals[hdr.index("Grid Size")],
            "block": vals[hdr.index("Block Size")], "stalls_per_issue": {}}
+    scale = {"Gbyte": 1e3, "Mbyte": 1.0, "Kbyte": 1e-3, "byte": 1e-6, "s": 1e3, "ms": 1.0, "us": 1e-3, "ns": 1e-6}
     for h, u, v in zip(hdr, units, vals):
         if h in KEYS:
             try:
-                res[KEYS[h]] = float(v)
+                f = float(v)
+                if KEYS[h].endswith("_MB") or KEYS[h].endswith("_ms"):
+                    f *= scale.get(u, 1.0)          # ncu picks the unit per value; normalise to MB / ms
+                res[KEYS[h]] = f
             except ValueError:
                 res[KEYS[h]] = v
         elif h.startswith(STALLS) and h.endswith("_per_issue_active.ratio"):
