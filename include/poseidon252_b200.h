@@ -153,6 +153,11 @@ int p252_merkle4_tree_nodes(size_t n_leaves, size_t* n_internal, int* n_levels);
  * (n_leaves/4 + n_leaves/16 + ... + 1 scalars); the root is the last element. */
 int p252_merkle4_build(p252_ctx* ctx, const p252_fr* leaves, size_t n_leaves, p252_fr* nodes_out, int flags);
 
+/* The same for arity 2 or 4 (node = Hash::digest(Domain::Merkle2 | Merkle4, children), src/hash.rs:22-31):
+ * internal nodes = (n_leaves - 1) / (arity - 1); n_leaves must be a power of the arity. */
+int p252_merkle_tree_nodes(int arity, size_t n_leaves, size_t* n_internal, int* n_levels);
+int p252_merkle_build(p252_ctx* ctx, int arity, const p252_fr* leaves, size_t n_leaves, p252_fr* nodes_out, int flags);
+
 /* ---- multi-GPU tree build: one process per GPU, one NCCL all-gather per level ---------------- */
 #define P252_NCCL_UNIQUE_ID_BYTES 128
 /* rank 0 creates the id and ships it to the other ranks by any means (torch.distributed / MPI) */

@@ -41,6 +41,8 @@ SIGNATURES = {
     "p252_merkle4_level": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p, c_int]),
     "p252_merkle4_tree_nodes": (c_int, [c_size_t, ctypes.POINTER(c_size_t), ctypes.POINTER(c_int)]),
     "p252_merkle4_build": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p, c_int]),
+    "p252_merkle_tree_nodes": (c_int, [c_int, c_size_t, ctypes.POINTER(c_size_t), ctypes.POINTER(c_int)]),
+    "p252_merkle_build": (c_int, [c_void_p, c_int, c_void_p, c_size_t, c_void_p, c_int]),
     "p252_dist_unique_id": (c_int, [c_void_p]),
     "p252_dist_init": (c_int, [c_void_p, c_void_p, c_int, c_int]),
     "p252_dist_finalize": (c_int, [c_void_p]),

@@ -549,29 +549,40 @@ int p252_merkle4_level(p252_ctx* ctx, const p252_fr* children, size_t n_parents,
     return p252_hash_batch(ctx, P252_DOMAIN_MERKLE4, children, n_parents, 4, parents, 1, flags);
 }
 
-int p252_merkle4_tree_nodes(size_t n_leaves, size_t* n_internal, int* n_levels) {
-    size_t m = n_leaves;
+static int merkle_domain(int arity) {
+    return arity == 4 ? P252_DOMAIN_MERKLE4 : (arity == 2 ? P252_DOMAIN_MERKLE2 : -1);
+}
+
+int p252_merkle_tree_nodes(int arity, size_t n_leaves, size_t* n_internal, int* n_levels) {
+    if (merkle_domain(arity) < 0) return P252_ERR_INVALID_ARGUMENT;
+    const size_t A = (size_t)arity;
+    size_t m = n_leaves, total = 0;
     int lv = 0;
     if (m == 0) return P252_ERR_INVALID_ARGUMENT;
     while (m > 1) {
-        if (m % 4) return P252_ERR_IO_PATTERN_VIOLATION;   // a level that is not a multiple of the arity
-        m /= 4;
+        if (m % A) return P252_ERR_IO_PATTERN_VIOLATION;   // a level that is not a multiple of the arity
+        m /= A;
+        total += m;
         ++lv;
     }
     if (lv == 0) return P252_ERR_INVALID_ARGUMENT;
-    if (n_internal) *n_internal = (n_leaves - 1) / 3;
+    if (n_internal) *n_internal = total;                 // (n_leaves - 1) / (arity - 1)
     if (n_levels) *n_levels = lv;
     return P252_OK;
 }
 
-static int merkle4_build_device(p252_ctx* ctx, const p252_fr* leaves, size_t n_leaves, p252_fr* nodes) {
+int p252_merkle4_tree_nodes(size_t n_leaves, size_t* n_internal, int* n_levels) {
+    return p252_merkle_tree_nodes(4, n_leaves, n_internal, n_levels);
+}
+
+static int merkle_build_device(p252_ctx* ctx, int arity, const p252_fr* leaves, size_t n_leaves, p252_fr* nodes) {
     p252_fr tag;
-    int rc = p252_hash_tag(P252_DOMAIN_MERKLE4, 4, 1, &tag);
+    int rc = p252_hash_tag(merkle_domain(arity), (size_t)arity, 1, &tag);
     if (rc != P252_OK) return rc;
     const p252_fr* src = leaves;
     p252_fr* dst = nodes;
-    for (size_t m = n_leaves / 4; m >= 1; m /= 4) {
-        cudaError_t le = p252::launch_digest(limbs(&tag), src, m, 4, dst, 1, false, ctx->stream);
+    for (size_t m = n_leaves / arity; m >= 1; m /= arity) {
+        cudaError_t le = p252::launch_digest(limbs(&tag), src, m, (uint32_t)arity, dst, 1, false, ctx->stream);
         if (le != cudaSuccess) return fail_cuda(ctx, le, "kernel launch");
         ctx->launches++;
         src = dst;
@@ -581,48 +592,52 @@ static int merkle4_build_device(p252_ctx* ctx, const p252_fr* leaves, size_t n_l
     return P252_OK;
 }
 
-int p252_merkle4_build(p252_ctx* ctx, const p252_fr* leaves, size_t n_leaves, p252_fr* nodes_out, int flags) {
+int p252_merkle_build(p252_ctx* ctx, int arity, const p252_fr* leaves, size_t n_leaves, p252_fr* nodes_out, int flags) {
     if (!ctx || !leaves || !nodes_out) return P252_ERR_INVALID_ARGUMENT;
     size_t n_internal;
-    int rc = p252_merkle4_tree_nodes(n_leaves, &n_internal, nullptr);
+    int rc = p252_merkle_tree_nodes(arity, n_leaves, &n_internal, nullptr);
     if (rc != P252_OK) return rc;
     DeviceGuard g(ctx->device);
     if (flags & P252_MEM_DEVICE) {
         if (!aligned16(leaves) || !aligned16(nodes_out)) return P252_ERR_INVALID_ARGUMENT;
-        rc = merkle4_build_device(ctx, leaves, n_leaves, nodes_out);
+        rc = merkle_build_device(ctx, arity, leaves, n_leaves, nodes_out);
         if (rc != P252_OK) return rc;
         if (!(flags & P252_ASYNC)) CU(cudaStreamSynchronize(ctx->stream));
         return P252_OK;
     }
     // HOST: the first (largest) level streams through the chunked pipeline straight from the host
-    // leaves; the remaining levels (1/4 of the work) run on the device-resident level.
+    // leaves; the remaining levels run on the device-resident level.
+    const size_t first = n_leaves / arity;
     p252_fr* d_nodes = nullptr;
     CU(cudaMalloc(reinterpret_cast<void**>(&d_nodes), n_internal * sizeof(p252_fr)));
     p252_fr tag;
-    p252_hash_tag(P252_DOMAIN_MERKLE4, 4, 1, &tag);
+    p252_hash_tag(merkle_domain(arity), (size_t)arity, 1, &tag);
     {
-        std::vector<Io> ios = {{leaves, nullptr, 128}, {nullptr, nodes_out, 32}};
+        std::vector<Io> ios = {{leaves, nullptr, (size_t)arity * 32}, {nullptr, nodes_out, 32}};
         size_t done = 0;   // the pipeline hands chunks in order; mirror each chunk into d_nodes as well
-        rc = run_host_pipeline(ctx, ios, n_leaves / 4, [&](void** d, size_t cnt, cudaStream_t st) {
-            cudaError_t e = p252::launch_digest(limbs(&tag), d[0], cnt, 4, d[1], 1, false, st);
+        rc = run_host_pipeline(ctx, ios, first, [&](void** d, size_t cnt, cudaStream_t st) {
+            cudaError_t e = p252::launch_digest(limbs(&tag), d[0], cnt, (uint32_t)arity, d[1], 1, false, st);
             if (e != cudaSuccess) return e;
             e = cudaMemcpyAsync(d_nodes + done, d[1], cnt * sizeof(p252_fr), cudaMemcpyDeviceToDevice, st);
             done += cnt;
             return e;
         });
     }
-    if (rc == P252_OK && n_leaves > 4) {
-        rc = merkle4_build_device(ctx, d_nodes, n_leaves / 4, d_nodes + n_leaves / 4);
+    if (rc == P252_OK && first > 1) {
+        rc = merkle_build_device(ctx, arity, d_nodes, first, d_nodes + first);
         if (rc == P252_OK) {
-            cudaError_t e = cudaMemcpyAsync(nodes_out + n_leaves / 4, d_nodes + n_leaves / 4,
-                                            (n_internal - n_leaves / 4) * sizeof(p252_fr), cudaMemcpyDeviceToHost,
-                                            ctx->stream);
+            cudaError_t e = cudaMemcpyAsync(nodes_out + first, d_nodes + first, (n_internal - first) * sizeof(p252_fr),
+                                            cudaMemcpyDeviceToHost, ctx->stream);
             if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
-            if (e != cudaSuccess) rc = fail_cuda(ctx, e, "merkle4 D2H");
+            if (e != cudaSuccess) rc = fail_cuda(ctx, e, "merkle D2H");
         }
     }
     cudaFree(d_nodes);
     return rc;
+}
+
+int p252_merkle4_build(p252_ctx* ctx, const p252_fr* leaves, size_t n_leaves, p252_fr* nodes_out, int flags) {
+    return p252_merkle_build(ctx, 4, leaves, n_leaves, nodes_out, flags);
 }
 
 // ---- multi-GPU ------------------------------------------------------------------------------------------

@@ -255,6 +255,16 @@ class Engine:
                                                  flags | (_native.ASYNC if async_ and flags else 0)))
         return res
 
+    def merkle_build(self, leaves, arity=4, out=None, async_=False):
+        """leaves (arity^k, 4) -> all internal nodes bottom-up, root last; arity 2 (Domain::Merkle2) or 4."""
+        lp, lead, flags, lk = self._in(leaves, (4,))
+        ni = ctypes.c_size_t(0)
+        self._check(self._lib.p252_merkle_tree_nodes(int(arity), lead[0], ctypes.byref(ni), None))
+        res = self._out_like(lk, (int(ni.value), 4)) if out is None else out
+        self._check(self._lib.p252_merkle_build(self._ctx, int(arity), lp, lead[0], self._ptr(res),
+                                                flags | (_native.ASYNC if async_ and flags else 0)))
+        return res
+
     # -- multi-GPU (one process per GPU) ----------------------------------------------------------
     def dist_unique_id(self):
         buf = (ctypes.c_uint8 * _native.NCCL_UNIQUE_ID_BYTES)()

@@ -15,15 +15,21 @@ def merkle4_build(leaves, engine=None, out=None, async_=False):
     return eng.merkle4_build(leaves, out=out, async_=async_)
 
 
-def level_offsets(n_leaves):
+def merkle2_build(leaves, engine=None, out=None, async_=False):
+    """Binary tree of Domain::Merkle2 digests (src/hash.rs:27-31): leaves (2^k, 4) -> internal nodes, root last."""
+    eng = engine or default_engine(leaves.device.index if hasattr(leaves, "is_cuda") else 0)
+    return eng.merkle_build(leaves, arity=2, out=out, async_=async_)
+
+
+def level_offsets(n_leaves, arity=4):
     """[(offset, size)] of each internal level inside the node array, bottom-up."""
-    out, off, m = [], 0, n_leaves // 4
+    out, off, m = [], 0, n_leaves // arity
     while m >= 1:
         out.append((off, m))
         off += m
         if m == 1:
             break
-        m //= 4
+        m //= arity
     return out
 
 

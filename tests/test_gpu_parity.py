@@ -310,3 +310,25 @@ def test_wire_format_roundtrip(engine, oracle):
     assert bool(dok.all()) and np.array_equal(dback.cpu().numpy().view(np.uint64), big)
     assert [int.from_bytes(r.tobytes(), "little") for r in db.cpu().numpy().view(np.uint8).reshape(-1, 32)[:5]] == \
         [int(v) for v in unmont(big[:5])]
+
+
+def test_merkle2_tree_vs_oracle(engine, oracle, coracle):
+    """Binary tree of Domain::Merkle2 nodes (src/hash.rs:27-31,49), host and device buffers."""
+    rng = np.random.default_rng(9)
+    n_leaves = 2 ** 9
+    leaves = random_limbs_fast(rng, n_leaves)
+    nodes = pb.merkle.merkle2_build(leaves, engine)
+    assert nodes.shape[0] == n_leaves - 1
+    tag = _tag(oracle, [oracle.Absorb(2), oracle.Squeeze(1)], oracle.Domain.Merkle2)
+    level = leaves
+    for off, m in pb.merkle.level_offsets(n_leaves, 2):
+        want = coracle.digest(tag, level.reshape(m, 2, 4), 2, 1).reshape(m, 4)
+        assert np.array_equal(nodes[off:off + m], want)
+        level = want
+    import torch
+    d = torch.from_numpy(leaves.view(np.int64)).cuda()
+    assert np.array_equal(engine.merkle_build(d, arity=2).cpu().numpy().view(np.uint64), nodes)
+    with pytest.raises(pb.IOPatternViolation):
+        engine.merkle_build(leaves[:48], arity=2)
+    with pytest.raises(pb.EngineError):
+        engine.merkle_build(leaves[:27], arity=3)
