@@ -332,3 +332,31 @@ def test_merkle2_tree_vs_oracle(engine, oracle, coracle):
         engine.merkle_build(leaves[:48], arity=2)
     with pytest.raises(pb.EngineError):
         engine.merkle_build(leaves[:27], arity=3)
+
+
+def test_randomized_shapes_vs_oracle(engine, oracle, coracle):
+    """Randomised sweep over (n, in_len, out_len) and (n, L): ragged batch sizes, multi-permutation absorbs and
+    squeezes, every result bit-exact against the C oracle."""
+    rng = np.random.default_rng(20260924)
+    for _ in range(24):
+        n = int(rng.choice([1, 2, 5, 31, 32, 33, 63, 100, 129, 300, 1025]))
+        in_len = int(rng.integers(1, 40))
+        out_len = int(rng.integers(1, 11))
+        data = random_limbs_fast(rng, (n, in_len))
+        got = pb.Hash.digest_batch(pb.Domain.Other, data, out_len, engine=engine)
+        tag = _tag(oracle, [oracle.Absorb(in_len), oracle.Squeeze(out_len)], oracle.Domain.Other)
+        assert np.array_equal(got, coracle.digest(tag, data, in_len, out_len)), (n, in_len, out_len)
+    for _ in range(12):
+        n = int(rng.choice([1, 3, 32, 65, 127, 500]))
+        L = int(rng.integers(1, 30))
+        msg, sec, non = random_limbs_fast(rng, (n, L)), random_limbs_fast(rng, (n, 2)), random_limbs_fast(rng, n)
+        tag = _tag(oracle, [oracle.Absorb(2), oracle.Absorb(1), oracle.Squeeze(L), oracle.Absorb(L), oracle.Squeeze(1)],
+                   oracle.Domain.Encryption)
+        c = pb.encrypt_batch(msg, sec, non, engine=engine)
+        assert np.array_equal(c, coracle.encrypt(tag, msg, L, sec, non)), (n, L)
+        m, ok = pb.decrypt_batch(c, sec, non, engine=engine)
+        assert ok.all() and np.array_equal(m, msg)
+    # worst-case style inputs: every limb all-ones below p, p-1, and values just below 2^255
+    special = mont([oracle.P - 1, oracle.P - 2, (1 << 254) + 12345, (1 << 255) % oracle.P, 1, 0])
+    states = np.stack([np.stack([special[(i + j) % 6] for j in range(5)]) for i in range(64)])
+    assert np.array_equal(engine.permute_batch(states), coracle.permute(states))
