@@ -190,7 +190,7 @@ def main():
     ap.add_argument("--steps", type=int, default=40)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="merkle4", choices=["merkle4", "encrypt", "permute", "sweep", "tree", "convert"])
+    ap.add_argument("--workload", default="merkle4", choices=["merkle4", "encrypt", "decrypt", "permute", "sweep", "tree", "convert"])
     ap.add_argument("--log2-batch", type=int, default=LOG2_BATCH)
     ap.add_argument("--log4-leaves", type=int, default=0, help="tree workload: 4^k leaves in the whole job (14 = BASELINE configs[3])")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -261,6 +261,19 @@ def main():
         perms_per_step, bytes_per_step = 2 * n, n * 256
         step = lambda i: pb.encrypt_batch(msg, sec, non, engine=eng, out=cip, async_=True)
         workload, l2_note = "encrypt_batch 2^%d messages, L=2 (benches/encrypt.rs:17)" % args.log2_batch, "256 MiB touched per step > L2"
+    elif args.workload == "decrypt":
+        with torch.cuda.stream(stream):
+            msg = torch.from_numpy(random_limbs_fast(rng, (n, 2)).view(np.int64)).cuda()
+            sec = torch.from_numpy(random_limbs_fast(rng, (n, 2)).view(np.int64)).cuda()
+            non = torch.from_numpy(random_limbs_fast(rng, (n,)).view(np.int64)).cuda()
+        cip = pb.encrypt_batch(msg, sec, non, engine=eng)
+        eng.sync()
+        perms_per_step, bytes_per_step = 2 * n, n * (192 + 64 + 1)
+        ok_holder = {}
+
+        def step(i):
+            ok_holder["m"], ok_holder["ok"] = pb.decrypt_batch(cip, sec, non, engine=eng, async_=True)
+        workload, l2_note = "decrypt_batch 2^%d ciphers, L=2 (benches/decrypt.rs:17)" % args.log2_batch, "257 MiB touched per step > L2"
     elif args.workload == "sweep":
         n = 1 << 18
         lens = [1, 2, 3, 4, 5, 8, 16, 32, 64, 128, 256]
@@ -369,7 +382,7 @@ def main():
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": ncu_traffic(), "peak_source": peak_src,
                 "kernel": "k_sponge_digest" if args.workload in ("merkle4", "sweep", "tree") else
-                          ("k_crypt<false>" if args.workload == "encrypt" else
+                          ("k_crypt<false>" if args.workload == "encrypt" else "k_crypt<true>" if args.workload == "decrypt" else
                            ("k_convert<false>" if args.workload == "convert" else "k_permute<false>")),
                 "algorithmic_bytes_per_launch": bytes_per_step // max(1, launches // args.steps),
                 "launch_ms": launch_ms,
