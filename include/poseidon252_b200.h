@@ -20,9 +20,12 @@
  *   - Every function returns a p252_status; nothing unwinds across the boundary.  Positive codes
  *     mirror dusk_poseidon::Error (src/error.rs:11-32); negative codes are engine failures.
  *   - There is NO CPU fallback: without a usable sm_100 device p252_create fails.
- *   - A context is bound to one device and one stream; calls on one context serialise; separate
- *     contexts are independent (the reference is stateless: ScalarPermutation is a ZST,
+ *   - A context is bound to one device and one stream; calls on one context serialise (a mutex
+ *     inside the context: concurrent callers block, they do not race); separate contexts are
+ *     independent (the reference is stateless: ScalarPermutation is a ZST,
  *     src/hades/permutation/scalar.rs:15).
+ *   - HOST calls are synchronous; on ANY exit path (success or failure) the staging streams are
+ *     joined, and for encrypt/decrypt the staging arenas (secrets, nonces, plaintext) are zeroed.
  */
 #ifndef POSEIDON252_B200_H
 #define POSEIDON252_B200_H
@@ -67,7 +70,14 @@ typedef enum p252_domain {
     P252_DOMAIN_OTHER = 3
 } p252_domain;
 
-enum { P252_MEM_HOST = 0, P252_MEM_DEVICE = 1, P252_ASYNC = 2 };
+enum {
+    P252_MEM_HOST = 0,
+    P252_MEM_DEVICE = 1,
+    P252_ASYNC = 2,
+    /* p252_merkle4_build_dist only (measurement aids, see p252_tree_level_timings): */
+    P252_TIMING = 4,     /* bracket every level's kernel and all-gather with CUDA events */
+    P252_NO_GATHER = 8   /* skip the collectives: compute-only timing run, node values above level 0 are NOT valid */
+};
 
 /* ---- library / context ------------------------------------------------------------------- */
 const char* p252_version(void);
@@ -89,6 +99,24 @@ uint64_t p252_launch_count(const p252_ctx* ctx);
 /* Pinned host memory for P252_MEM_HOST callers that want full PCIe bandwidth. */
 int p252_host_alloc(size_t bytes, void** out);
 int p252_host_free(void* p);
+
+/* Static facts about the kernels of this build (what one Hades permutation costs in this formulation; used by
+ * benchmarks to state the integer-multiplier roofline next to the HBM one).  Set struct_size before the call. */
+typedef struct p252_kernel_info {
+    uint32_t struct_size;
+    uint32_t wide_mul_per_permutation; /* 32x32->64 multiply instructions (IMAD.WIDE / IMAD.HI) per permutation */
+    uint32_t dfma_per_permutation;     /* FP64 FMAs of the small-integer MDS layer per permutation              */
+    uint32_t montmul_per_permutation;  /* Montgomery products incl. squarings (365; the reference does 2000)    */
+    uint32_t threads_per_block;
+    uint32_t min_blocks_per_sm;
+} p252_kernel_info;
+int p252_get_kernel_info(p252_kernel_info* out);
+
+/* Fault injection / inspection for tests (no effect unless called).  p252_debug_fail_chunk: the k-th staged chunk
+ * (0-based) of the NEXT host-buffer call on this context fails as if its kernel launch had failed (one shot).
+ * p252_debug_staging_nonzero: number of non-zero bytes currently held by the context's staging arenas. */
+int p252_debug_fail_chunk(p252_ctx* ctx, long long k);
+int p252_debug_staging_nonzero(p252_ctx* ctx, size_t* nonzero_bytes);
 
 /* ---- host-side sponge bookkeeping (no GPU needed) ----------------------------------------- */
 /* u64::from(Domain), src/hash.rs:43-55 */
@@ -139,8 +167,10 @@ int p252_scalars_to_bytes(p252_ctx* ctx, const p252_fr* in, size_t n, uint8_t* b
 int p252_encrypt_batch(p252_ctx* ctx, const p252_fr* msg, size_t n, size_t L, const p252_fr* secret_uv,
                        const p252_fr* nonce, p252_fr* cipher, int flags);
 /* decrypt_batch (src/encryption.rs:83-95).  cipher: n x (L+1), msg: n x L, ok: n bytes; ok[i] = 0
- * <=> the reference returns Error::DecryptionFailed for item i (its msg is zeroed).  Returns
- * P252_OK even when some items fail; *n_failed (optional) receives their count (HOST flags only). */
+ * <=> the reference returns Error::DecryptionFailed for item i (its msg is zeroed; device callers must look at
+ * ok[i] before trusting msg[i]).  Returns P252_OK even when some items fail; *n_failed (optional, a HOST pointer
+ * for both memory spaces) receives their count -- for device buffers it is counted on the device and, with
+ * P252_ASYNC, written by an asynchronous copy that is complete after p252_sync. */
 int p252_decrypt_batch(p252_ctx* ctx, const p252_fr* cipher, size_t n, size_t L, const p252_fr* secret_uv,
                        const p252_fr* nonce, p252_fr* msg, uint8_t* ok, size_t* n_failed, int flags);
 
@@ -157,6 +187,22 @@ int p252_merkle4_build(p252_ctx* ctx, const p252_fr* leaves, size_t n_leaves, p2
  * internal nodes = (n_leaves - 1) / (arity - 1); n_leaves must be a power of the arity. */
 int p252_merkle_tree_nodes(int arity, size_t n_leaves, size_t* n_internal, int* n_levels);
 int p252_merkle_build(p252_ctx* ctx, int arity, const p252_fr* leaves, size_t n_leaves, p252_fr* nodes_out, int flags);
+
+/* ---- Merkle openings (consumer: poseidon-merkle `Opening`, AGENTS.md:62-66; node hash src/hash.rs:22-31) ------
+ * A tree is `leaves` (n_leaves = arity^depth) + `nodes` as written by p252_merkle_build.  The opening of leaf i
+ * holds, for every level l = 0..depth-1 (0 = the leaf level), the WHOLE sibling group of the path node: the
+ * `arity` items at [g*arity, (g+1)*arity) of level l with g = i / arity^(l+1); the path node sits at offset
+ * (i / arity^l) % arity inside its group.  Empty slots of a sparse tree are the zero scalar (src/hash.rs:22-31).
+ * paths: n x depth x arity scalars, item-major.  leaf_idx lives in the same memory space as the other buffers. */
+int p252_merkle_open_batch(p252_ctx* ctx, int arity, const p252_fr* leaves, size_t n_leaves, const p252_fr* nodes,
+                           const uint64_t* leaf_idx, size_t n, p252_fr* paths_out, int flags);
+/* n x Opening::verify: cur = leaf_items[i]; for every level: paths[i][l][pos] must equal cur, then
+ * cur = Hash::digest(Domain::Merkle{arity}, paths[i][l]); finally cur must equal *root.  ok[i] = 1 iff all hold
+ * (depth permutations per item, fused with the checks in one kernel).  root is a HOST pointer; *n_failed as in
+ * p252_decrypt_batch. */
+int p252_merkle_verify_batch(p252_ctx* ctx, int arity, int depth, const p252_fr* leaf_items, const uint64_t* leaf_idx,
+                             const p252_fr* paths, const p252_fr* root, size_t n, uint8_t* ok, size_t* n_failed,
+                             int flags);
 
 /* ---- multi-GPU tree build: one process per GPU, one NCCL all-gather per level ---------------- */
 #define P252_NCCL_UNIQUE_ID_BYTES 128
@@ -183,6 +229,17 @@ int p252_merkle4_shard_plan(size_t n_leaves_total, int nranks, int rank, p252_le
  * nodes_out (same space as leaves_shard): all internal levels as in p252_merkle4_build. */
 int p252_merkle4_build_dist(p252_ctx* ctx, const p252_fr* leaves_shard, size_t n_leaves_total, p252_fr* nodes_out,
                             int flags);
+/* Per-level device times of the last p252_merkle4_build_dist(... | P252_TIMING) on this context (synchronises
+ * the context first): kernel_ms on the compute stream, gather_ms / gather_bytes of that level's all-gather on the
+ * communication stream (0 for levels computed redundantly), and total_ms from the first kernel to the last event. */
+typedef struct p252_level_timing {
+    uint64_t nodes;        /* nodes of the level                      */
+    uint64_t my_nodes;     /* nodes this rank hashed                  */
+    uint64_t gather_bytes; /* bytes this rank received + kept (level) */
+    float kernel_ms;
+    float gather_ms;
+} p252_level_timing;
+int p252_tree_level_timings(p252_ctx* ctx, p252_level_timing* levels, int capacity, int* n_levels, float* total_ms);
 
 #ifdef __cplusplus
 }

@@ -43,11 +43,14 @@ def permute(states, threads=1):
     return s
 
 
-def digest(tag, inp, in_len, out_len=1, threads=1):
+def digest(tag, inp, in_len, out_len=1, threads=1, out=None):
+    """out: optional preallocated (n, out_len, 4) uint64 array (lets a caller time the C call alone)."""
     tag = _c(tag).reshape(4)
     inp = _c(inp).reshape(-1, in_len, 4)
     n = inp.shape[0]
-    out = np.zeros((n, out_len, 4), dtype=np.uint64)
+    if out is None:
+        out = np.zeros((n, out_len, 4), dtype=np.uint64)
+    assert out.dtype == np.uint64 and out.flags.c_contiguous and out.shape == (n, out_len, 4)
     if threads > 1:
         lib().oracle_digest_mt(_p(tag), _p(inp), ctypes.c_size_t(n), ctypes.c_size_t(in_len), _p(out),
                                ctypes.c_size_t(out_len), ctypes.c_int(threads))

@@ -43,6 +43,13 @@ SIGNATURES = {
     "p252_merkle4_build": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p, c_int]),
     "p252_merkle_tree_nodes": (c_int, [c_int, c_size_t, ctypes.POINTER(c_size_t), ctypes.POINTER(c_int)]),
     "p252_merkle_build": (c_int, [c_void_p, c_int, c_void_p, c_size_t, c_void_p, c_int]),
+    "p252_get_kernel_info": (c_int, [c_void_p]),
+    "p252_debug_fail_chunk": (c_int, [c_void_p, ctypes.c_longlong]),
+    "p252_debug_staging_nonzero": (c_int, [c_void_p, ctypes.POINTER(c_size_t)]),
+    "p252_merkle_open_batch": (c_int, [c_void_p, c_int, c_void_p, c_size_t, c_void_p, c_void_p, c_size_t, c_void_p, c_int]),
+    "p252_merkle_verify_batch": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p,
+                                         ctypes.POINTER(c_size_t), c_int]),
+    "p252_tree_level_timings": (c_int, [c_void_p, c_void_p, c_int, ctypes.POINTER(c_int), ctypes.POINTER(ctypes.c_float)]),
     "p252_dist_unique_id": (c_int, [c_void_p]),
     "p252_dist_init": (c_int, [c_void_p, c_void_p, c_int, c_int]),
     "p252_dist_finalize": (c_int, [c_void_p]),
@@ -50,7 +57,20 @@ SIGNATURES = {
     "p252_merkle4_build_dist": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p, c_int]),
 }
 
-MEM_HOST, MEM_DEVICE, ASYNC = 0, 1, 2
+MEM_HOST, MEM_DEVICE, ASYNC, TIMING, NO_GATHER = 0, 1, 2, 4, 8
+
+
+class KernelInfo(ctypes.Structure):
+    """p252_kernel_info"""
+    _fields_ = [("struct_size", ctypes.c_uint32), ("wide_mul_per_permutation", ctypes.c_uint32),
+                ("dfma_per_permutation", ctypes.c_uint32), ("montmul_per_permutation", ctypes.c_uint32),
+                ("threads_per_block", ctypes.c_uint32), ("min_blocks_per_sm", ctypes.c_uint32)]
+
+
+class LevelTiming(ctypes.Structure):
+    """p252_level_timing"""
+    _fields_ = [("nodes", ctypes.c_uint64), ("my_nodes", ctypes.c_uint64), ("gather_bytes", ctypes.c_uint64),
+                ("kernel_ms", ctypes.c_float), ("gather_ms", ctypes.c_float)]
 
 
 class LevelPlan(ctypes.Structure):

@@ -14,6 +14,7 @@
 #include <algorithm>
 #include <cstdio>
 #include <cstring>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -44,12 +45,30 @@ struct p252_ctx {
     cudaEvent_t ev_join[kSlots] = {nullptr, nullptr, nullptr};
     uint64_t launches = 0;
     std::string last_error;
+    // calls on one context serialise (recursive: public entry points call each other)
+    std::recursive_mutex mu;
+    // device-side failure counter (decrypt / opening verification on DEVICE buffers) + its pinned mirror
+    unsigned long long* d_counter = nullptr;
+    unsigned long long* h_counter = nullptr;
+    // test hook: index of the staged chunk that fails in the next host-buffer call (-1 = none)
+    long long fail_chunk = -1;
     // multi-GPU
     ncclComm_t comm = nullptr;
     int rank = 0, nranks = 1;
     cudaStream_t comm_stream = nullptr;
     cudaEvent_t ev_level = nullptr, ev_comm = nullptr;
+    // per-level timing of the last P252_TIMING tree build
+    struct LevelEvents {
+        cudaEvent_t k0 = nullptr, k1 = nullptr, g0 = nullptr, g1 = nullptr;
+    };
+    std::vector<LevelEvents> level_events;
+    std::vector<p252_level_timing> level_info;   // static part (nodes, bytes) of the last timed build
+    std::vector<char> level_gathered;
+    int timed_levels = 0;
+    cudaEvent_t ev_tree_end = nullptr;
 };
+
+#define P252_LOCK(ctx) std::lock_guard<std::recursive_mutex> lock__((ctx)->mu)
 
 namespace {
 
@@ -130,8 +149,11 @@ struct Io {
     size_t item_bytes;   // bytes per batch item
 };
 
-// wipe = true: the staging arenas held secrets (shared secret, nonce, plaintext); clear them before returning
-// (the reference's dependencies zeroize sponge state, Cargo.toml:15,17 "zeroize").
+// wipe = true: the staging arenas held secrets (shared secret, nonce, plaintext); they are cleared before
+// returning (the reference's dependencies zeroize sponge state, Cargo.toml:15,17 "zeroize").
+// Whatever happens inside the chunk loop, the common exit below runs: slot streams are joined back into the
+// context stream, the arenas are wiped if asked, and the call returns only after everything enqueued has
+// finished -- so on an error no copy into the caller's buffers is still in flight and no secret is left staged.
 template <typename Launch>
 int run_host_pipeline(p252_ctx* ctx, std::vector<Io>& ios, size_t n, Launch launch, bool wipe = false) {
     if (n == 0) return P252_OK;
@@ -140,49 +162,73 @@ int run_host_pipeline(p252_ctx* ctx, std::vector<Io>& ios, size_t n, Launch laun
     size_t chunk = std::max<size_t>(1024, std::min(kChunkItemsMax, kChunkBytesTarget / std::max<size_t>(per_item, 1)));
     chunk = (chunk + 127) / 128 * 128;
     if (chunk > n) chunk = n;
-    // fork: slots wait for everything already enqueued on the context stream
-    CU(cudaEventRecord(ctx->ev_fork, ctx->stream));
-    for (int s = 0; s < kSlots; ++s) CU(cudaStreamWaitEvent(ctx->slots[s].stream, ctx->ev_fork, 0));
-    size_t k = 0;
-    for (size_t off = 0; off < n; off += chunk, ++k) {
-        const size_t cnt = std::min(chunk, n - off);
-        Slot& sl = ctx->slots[k % kSlots];
-        // arena layout: one 256-byte aligned region per buffer
-        size_t need = 0;
-        for (auto& io : ios) need += (chunk * io.item_bytes + 255) / 256 * 256;
-        if (sl.arena_bytes < need) {
-            CU(cudaStreamSynchronize(sl.stream));
-            if (sl.arena) CU(cudaFree(sl.arena));
-            sl.arena = nullptr;
-            sl.arena_bytes = 0;
-            CU(cudaMalloc(&sl.arena, need));
-            sl.arena_bytes = need;
+    const long long fail_at = ctx->fail_chunk;
+    ctx->fail_chunk = -1;                                  // one shot
+
+    auto body = [&]() -> int {
+        // fork: slots wait for everything already enqueued on the context stream
+        CU(cudaEventRecord(ctx->ev_fork, ctx->stream));
+        for (int s = 0; s < kSlots; ++s) CU(cudaStreamWaitEvent(ctx->slots[s].stream, ctx->ev_fork, 0));
+        size_t k = 0;
+        for (size_t off = 0; off < n; off += chunk, ++k) {
+            const size_t cnt = std::min(chunk, n - off);
+            Slot& sl = ctx->slots[k % kSlots];
+            // arena layout: one 256-byte aligned region per buffer
+            size_t need = 0;
+            for (auto& io : ios) need += (chunk * io.item_bytes + 255) / 256 * 256;
+            if (sl.arena_bytes < need) {
+                CU(cudaStreamSynchronize(sl.stream));
+                if (sl.arena) {
+                    if (wipe) CU(cudaMemset(sl.arena, 0, sl.arena_bytes));
+                    CU(cudaFree(sl.arena));
+                }
+                sl.arena = nullptr;
+                sl.arena_bytes = 0;
+                CU(cudaMalloc(&sl.arena, need));
+                sl.arena_bytes = need;
+            }
+            std::vector<void*> d(ios.size());
+            size_t pos = 0;
+            for (size_t b = 0; b < ios.size(); ++b) {
+                d[b] = static_cast<uint8_t*>(sl.arena) + pos;
+                pos += (chunk * ios[b].item_bytes + 255) / 256 * 256;
+                if (ios[b].h_in)
+                    CU(cudaMemcpyAsync(d[b], static_cast<const uint8_t*>(ios[b].h_in) + off * ios[b].item_bytes,
+                                       cnt * ios[b].item_bytes, cudaMemcpyHostToDevice, sl.stream));
+            }
+            cudaError_t le = ((long long)k == fail_at) ? cudaErrorLaunchFailure : launch(d.data(), cnt, sl.stream);
+            if (le != cudaSuccess) return fail_cuda(ctx, le, (long long)k == fail_at ? "kernel launch (injected fault)" : "kernel launch");
+            ctx->launches++;
+            for (size_t b = 0; b < ios.size(); ++b)
+                if (ios[b].h_out)
+                    CU(cudaMemcpyAsync(static_cast<uint8_t*>(ios[b].h_out) + off * ios[b].item_bytes, d[b],
+                                       cnt * ios[b].item_bytes, cudaMemcpyDeviceToHost, sl.stream));
         }
-        std::vector<void*> d(ios.size());
-        size_t pos = 0;
-        for (size_t b = 0; b < ios.size(); ++b) {
-            d[b] = static_cast<uint8_t*>(sl.arena) + pos;
-            pos += (chunk * ios[b].item_bytes + 255) / 256 * 256;
-            if (ios[b].h_in)
-                CU(cudaMemcpyAsync(d[b], static_cast<const uint8_t*>(ios[b].h_in) + off * ios[b].item_bytes,
-                                   cnt * ios[b].item_bytes, cudaMemcpyHostToDevice, sl.stream));
-        }
-        cudaError_t le = launch(d.data(), cnt, sl.stream);
-        if (le != cudaSuccess) return fail_cuda(ctx, le, "kernel launch");
-        ctx->launches++;
-        for (size_t b = 0; b < ios.size(); ++b)
-            if (ios[b].h_out)
-                CU(cudaMemcpyAsync(static_cast<uint8_t*>(ios[b].h_out) + off * ios[b].item_bytes, d[b],
-                                   cnt * ios[b].item_bytes, cudaMemcpyDeviceToHost, sl.stream));
-    }
-    // join: the context stream continues after every slot
+        return P252_OK;
+    };
+    int rc = body();
+
+    // ---- common exit (success and failure): wipe, join, drain --------------------------------------------------
+    const std::string first_error = ctx->last_error;
+    cudaError_t ce = cudaSuccess;
+    auto keep = [&](cudaError_t e) {
+        if (e != cudaSuccess && ce == cudaSuccess) ce = e;
+    };
     for (int s = 0; s < kSlots; ++s) {
-        if (wipe && ctx->slots[s].arena)
-            CU(cudaMemsetAsync(ctx->slots[s].arena, 0, ctx->slots[s].arena_bytes, ctx->slots[s].stream));
-        CU(cudaEventRecord(ctx->ev_join[s], ctx->slots[s].stream));
-        CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_join[s], 0));
+        Slot& sl = ctx->slots[s];
+        if (wipe && sl.arena) keep(cudaMemsetAsync(sl.arena, 0, sl.arena_bytes, sl.stream));
+        keep(cudaEventRecord(ctx->ev_join[s], sl.stream));
+        keep(cudaStreamWaitEvent(ctx->stream, ctx->ev_join[s], 0));
     }
-    CU(cudaStreamSynchronize(ctx->stream));   // HOST calls are synchronous on return, like the reference
+    keep(cudaStreamSynchronize(ctx->stream));   // HOST calls are synchronous on return, like the reference
+    if (rc != P252_OK) {
+        // make sure nothing is in flight even if the join itself could not be enqueued
+        for (int s = 0; s < kSlots; ++s) cudaStreamSynchronize(ctx->slots[s].stream);
+        cudaGetLastError();
+        ctx->last_error = first_error;
+        return rc;
+    }
+    if (ce != cudaSuccess) return fail_cuda(ctx, ce, "host pipeline join");
     return P252_OK;
 }
 
@@ -190,6 +236,30 @@ int finish_device_call(p252_ctx* ctx, cudaError_t le, int flags) {
     if (le != cudaSuccess) return fail_cuda(ctx, le, "kernel launch");
     ctx->launches++;
     if (!(flags & P252_ASYNC)) CU(cudaStreamSynchronize(ctx->stream));
+    return P252_OK;
+}
+
+// DEVICE-buffer calls that count failures on the device: zero the counter before the launch ...
+int counter_begin(p252_ctx* ctx) {
+    CU(cudaMemsetAsync(ctx->d_counter, 0, sizeof(unsigned long long), ctx->stream));
+    return P252_OK;
+}
+void CUDART_CB publish_counter(void* arg) {
+    auto* pr = static_cast<std::pair<const unsigned long long*, size_t*>*>(arg);
+    *pr->second = (size_t)*pr->first;
+    delete pr;
+}
+// ... and after it copy the counter to the pinned mirror and from there to the caller's size_t (a host function on
+// the stream, so that P252_ASYNC callers see it after p252_sync).
+int counter_end(p252_ctx* ctx, size_t* n_failed) {
+    if (!n_failed) return P252_OK;
+    CU(cudaMemcpyAsync(ctx->h_counter, ctx->d_counter, sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
+    auto* pr = new std::pair<const unsigned long long*, size_t*>(ctx->h_counter, n_failed);
+    cudaError_t e = cudaLaunchHostFunc(ctx->stream, publish_counter, pr);
+    if (e != cudaSuccess) {
+        delete pr;
+        return fail_cuda(ctx, e, "cudaLaunchHostFunc");
+    }
     return P252_OK;
 }
 
@@ -283,6 +353,12 @@ int p252_create_on_stream(int device, void* cuda_stream, p252_ctx** out) {
         return bail(e, "cudaEventCreate");
     if ((e = cudaEventCreateWithFlags(&ctx->ev_comm, cudaEventDisableTiming)) != cudaSuccess)
         return bail(e, "cudaEventCreate");
+    if ((e = cudaEventCreate(&ctx->ev_tree_end)) != cudaSuccess) return bail(e, "cudaEventCreate");
+    if ((e = cudaMalloc(reinterpret_cast<void**>(&ctx->d_counter), sizeof(unsigned long long))) != cudaSuccess)
+        return bail(e, "cudaMalloc");
+    if ((e = cudaHostAlloc(reinterpret_cast<void**>(&ctx->h_counter), sizeof(unsigned long long), cudaHostAllocPortable)) != cudaSuccess)
+        return bail(e, "cudaHostAlloc");
+    *ctx->h_counter = 0;
     *out = ctx;
     return P252_OK;
 }
@@ -305,17 +381,59 @@ void p252_destroy(p252_ctx* ctx) {
     if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
     if (ctx->ev_level) cudaEventDestroy(ctx->ev_level);
     if (ctx->ev_comm) cudaEventDestroy(ctx->ev_comm);
-    if (ctx->own_stream && ctx->stream) {
-        cudaStreamSynchronize(ctx->stream);
-        cudaStreamDestroy(ctx->stream);
-    }
+    if (ctx->ev_tree_end) cudaEventDestroy(ctx->ev_tree_end);
+    for (auto& le : ctx->level_events)
+        for (cudaEvent_t ev : {le.k0, le.k1, le.g0, le.g1})
+            if (ev) cudaEventDestroy(ev);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);   // pending host functions reference h_counter
+    if (ctx->d_counter) cudaFree(ctx->d_counter);
+    if (ctx->h_counter) cudaFreeHost(ctx->h_counter);
+    if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
 
 int p252_sync(p252_ctx* ctx) {
     if (!ctx) return P252_ERR_INVALID_ARGUMENT;
+    P252_LOCK(ctx);
     DeviceGuard g(ctx->device);
     CU(cudaStreamSynchronize(ctx->stream));
+    return P252_OK;
+}
+
+int p252_get_kernel_info(p252_kernel_info* out) {
+    if (!out || out->struct_size < sizeof(p252_kernel_info)) return P252_ERR_INVALID_ARGUMENT;
+    int t = 0, b = 0;
+    p252::kernel_launch_shape(&t, &b);
+    out->struct_size = (uint32_t)sizeof(p252_kernel_info);
+    out->wide_mul_per_permutation = p252::wide_mul_per_permutation();
+    out->dfma_per_permutation = p252::dfma_per_permutation();
+    out->montmul_per_permutation = 365;
+    out->threads_per_block = (uint32_t)t;
+    out->min_blocks_per_sm = (uint32_t)b;
+    return P252_OK;
+}
+
+int p252_debug_fail_chunk(p252_ctx* ctx, long long k) {
+    if (!ctx) return P252_ERR_INVALID_ARGUMENT;
+    P252_LOCK(ctx);
+    ctx->fail_chunk = k;
+    return P252_OK;
+}
+
+int p252_debug_staging_nonzero(p252_ctx* ctx, size_t* nonzero_bytes) {
+    if (!ctx || !nonzero_bytes) return P252_ERR_INVALID_ARGUMENT;
+    P252_LOCK(ctx);
+    DeviceGuard g(ctx->device);
+    size_t bad = 0;
+    for (int s = 0; s < kSlots; ++s) {
+        Slot& sl = ctx->slots[s];
+        if (!sl.arena) continue;
+        CU(cudaStreamSynchronize(sl.stream));
+        std::vector<uint8_t> h(sl.arena_bytes);
+        CU(cudaMemcpy(h.data(), sl.arena, sl.arena_bytes, cudaMemcpyDeviceToHost));
+        for (uint8_t v : h) bad += v ? 1 : 0;
+    }
+    *nonzero_bytes = bad;
     return P252_OK;
 }
 
@@ -412,6 +530,7 @@ int p252_encryption_tag(size_t L, p252_fr* tag) {
 // ---- batch entry points ---------------------------------------------------------------------------
 static int permute_impl(p252_ctx* ctx, p252_fr* states, size_t n, int flags, bool dense) {
     if (!ctx || (!states && n)) return P252_ERR_INVALID_ARGUMENT;
+    P252_LOCK(ctx);
     DeviceGuard g(ctx->device);
     if (flags & P252_MEM_DEVICE) {
         if (!aligned16(states)) return P252_ERR_INVALID_ARGUMENT;
@@ -436,6 +555,7 @@ static int digest_impl(p252_ctx* ctx, const p252_fr* tag, const p252_fr* in, siz
     if (!ctx || !tag || ((!in || !out) && n)) return P252_ERR_INVALID_ARGUMENT;
     if (in_len == 0 || out_len == 0) return P252_ERR_INVALID_IO_PATTERN;
     if (in_len > 0x7fffffffull / 32 || out_len > 0x7fffffffull / 32) return P252_ERR_INVALID_ARGUMENT;
+    P252_LOCK(ctx);
     DeviceGuard g(ctx->device);
     const uint32_t il = (uint32_t)in_len, ol = (uint32_t)out_len;
     if (flags & P252_MEM_DEVICE) {
@@ -472,6 +592,7 @@ int p252_hash_batch_truncated(p252_ctx* ctx, int domain, const p252_fr* in, size
 
 static int convert_impl(p252_ctx* ctx, const void* in, size_t n, void* out, uint8_t* ok, int flags, bool from_bytes) {
     if (!ctx || ((!in || !out) && n)) return P252_ERR_INVALID_ARGUMENT;
+    P252_LOCK(ctx);
     DeviceGuard g(ctx->device);
     if (flags & P252_MEM_DEVICE) {
         if (!aligned16(in) || !aligned16(out)) return P252_ERR_INVALID_ARGUMENT;
@@ -499,6 +620,7 @@ int p252_encrypt_batch(p252_ctx* ctx, const p252_fr* msg, size_t n, size_t L, co
     p252_fr tag;
     int rc = p252_encryption_tag(L, &tag);
     if (rc != P252_OK) return rc;
+    P252_LOCK(ctx);
     DeviceGuard g(ctx->device);
     const uint32_t l32 = (uint32_t)L;
     if (flags & P252_MEM_DEVICE) {
@@ -521,20 +643,27 @@ int p252_decrypt_batch(p252_ctx* ctx, const p252_fr* cipher, size_t n, size_t L,
     p252_fr tag;
     int rc = p252_encryption_tag(L, &tag);
     if (rc != P252_OK) return rc;
+    P252_LOCK(ctx);
     DeviceGuard g(ctx->device);
     const uint32_t l32 = (uint32_t)L;
     if (flags & P252_MEM_DEVICE) {
         if (!aligned16(cipher) || !aligned16(secret_uv) || !aligned16(nonce) || !aligned16(msg))
             return P252_ERR_INVALID_ARGUMENT;
-        if (n_failed) *n_failed = 0;   // not computed for device buffers (ok[] stays on the device)
+        if (n_failed) *n_failed = 0;
         if (n == 0) return P252_OK;
-        return finish_device_call(
-            ctx, p252::launch_decrypt(limbs(&tag), cipher, n, l32, secret_uv, nonce, msg, ok, ctx->stream), flags);
+        if (n_failed && (rc = counter_begin(ctx)) != P252_OK) return rc;
+        cudaError_t le = p252::launch_decrypt(limbs(&tag), cipher, n, l32, secret_uv, nonce, msg, ok,
+                                              n_failed ? ctx->d_counter : nullptr, ctx->stream);
+        if (le != cudaSuccess) return fail_cuda(ctx, le, "kernel launch");
+        ctx->launches++;
+        if ((rc = counter_end(ctx, n_failed)) != P252_OK) return rc;
+        if (!(flags & P252_ASYNC)) CU(cudaStreamSynchronize(ctx->stream));
+        return P252_OK;
     }
     std::vector<Io> ios = {{cipher, nullptr, (L + 1) * 32}, {secret_uv, nullptr, 64}, {nonce, nullptr, 32},
                            {nullptr, msg, L * 32}, {nullptr, ok, 1}};
     rc = run_host_pipeline(ctx, ios, n, [&](void** d, size_t cnt, cudaStream_t st) {
-        return p252::launch_decrypt(limbs(&tag), d[0], cnt, l32, d[1], d[2], d[3], static_cast<uint8_t*>(d[4]), st);
+        return p252::launch_decrypt(limbs(&tag), d[0], cnt, l32, d[1], d[2], d[3], static_cast<uint8_t*>(d[4]), nullptr, st);
     }, /*wipe=*/true);
     if (rc == P252_OK && n_failed) {
         size_t bad = 0;
@@ -597,6 +726,7 @@ int p252_merkle_build(p252_ctx* ctx, int arity, const p252_fr* leaves, size_t n_
     size_t n_internal;
     int rc = p252_merkle_tree_nodes(arity, n_leaves, &n_internal, nullptr);
     if (rc != P252_OK) return rc;
+    P252_LOCK(ctx);
     DeviceGuard g(ctx->device);
     if (flags & P252_MEM_DEVICE) {
         if (!aligned16(leaves) || !aligned16(nodes_out)) return P252_ERR_INVALID_ARGUMENT;
@@ -640,6 +770,93 @@ int p252_merkle4_build(p252_ctx* ctx, const p252_fr* leaves, size_t n_leaves, p2
     return p252_merkle_build(ctx, 4, leaves, n_leaves, nodes_out, flags);
 }
 
+// ---- Merkle openings ----------------------------------------------------------------------------------------
+static int tree_depth(int arity, size_t n_leaves, int* depth) {
+    int lv = 0;
+    int rc = p252_merkle_tree_nodes(arity, n_leaves, nullptr, &lv);
+    if (rc != P252_OK) return rc;
+    *depth = lv;
+    return P252_OK;
+}
+
+int p252_merkle_open_batch(p252_ctx* ctx, int arity, const p252_fr* leaves, size_t n_leaves, const p252_fr* nodes,
+                           const uint64_t* leaf_idx, size_t n, p252_fr* paths_out, int flags) {
+    if (!ctx || !leaves || !nodes || ((!leaf_idx || !paths_out) && n)) return P252_ERR_INVALID_ARGUMENT;
+    int depth = 0;
+    int rc = tree_depth(arity, n_leaves, &depth);
+    if (rc != P252_OK) return rc;
+    P252_LOCK(ctx);
+    DeviceGuard g(ctx->device);
+    if (flags & P252_MEM_DEVICE) {
+        if (!aligned16(leaves) || !aligned16(nodes) || !aligned16(paths_out) || (reinterpret_cast<uintptr_t>(leaf_idx) & 7))
+            return P252_ERR_INVALID_ARGUMENT;
+        if (n == 0) return P252_OK;
+        return finish_device_call(ctx, p252::launch_merkle_open(leaves, nodes, leaf_idx, n, arity, (uint32_t)depth,
+                                                                n_leaves, paths_out, ctx->stream), flags);
+    }
+    // HOST tree: an opening is a pure gather of 32-byte items the caller already holds in host memory -- shipping
+    // the whole tree to the GPU to copy depth*arity scalars back would only add PCIe traffic.  No hashing happens here.
+    std::vector<size_t> off((size_t)depth, 0);       // offset of internal level l-1 inside nodes, for l >= 1
+    {
+        size_t m = n_leaves / (size_t)arity, acc = 0;
+        for (int l = 1; l < depth; ++l, m /= (size_t)arity) {
+            off[(size_t)l] = acc;
+            acc += m;
+        }
+    }
+    for (size_t i = 0; i < n; ++i)
+        if (leaf_idx[i] >= n_leaves) return P252_ERR_INVALID_ARGUMENT;
+    const size_t A = (size_t)arity;
+    for (size_t i = 0; i < n; ++i) {
+        uint64_t idx = leaf_idx[i];
+        for (int l = 0; l < depth; ++l) {
+            const uint64_t group = idx / A;
+            const p252_fr* src = (l == 0) ? leaves + group * A : nodes + off[(size_t)l] + group * A;
+            memcpy(paths_out + (i * (size_t)depth + (size_t)l) * A, src, A * sizeof(p252_fr));
+            idx = group;
+        }
+    }
+    return P252_OK;
+}
+
+int p252_merkle_verify_batch(p252_ctx* ctx, int arity, int depth, const p252_fr* leaf_items, const uint64_t* leaf_idx,
+                             const p252_fr* paths, const p252_fr* root, size_t n, uint8_t* ok, size_t* n_failed,
+                             int flags) {
+    if (!ctx || !root || ((!leaf_items || !leaf_idx || !paths || !ok) && n)) return P252_ERR_INVALID_ARGUMENT;
+    if (merkle_domain(arity) < 0 || depth < 1 || depth > 64) return P252_ERR_INVALID_ARGUMENT;
+    p252_fr tag;
+    int rc = p252_hash_tag(merkle_domain(arity), (size_t)arity, 1, &tag);
+    if (rc != P252_OK) return rc;
+    P252_LOCK(ctx);
+    DeviceGuard g(ctx->device);
+    if (n_failed) *n_failed = 0;
+    if (flags & P252_MEM_DEVICE) {
+        if (!aligned16(leaf_items) || !aligned16(paths) || (reinterpret_cast<uintptr_t>(leaf_idx) & 7))
+            return P252_ERR_INVALID_ARGUMENT;
+        if (n == 0) return P252_OK;
+        if (n_failed && (rc = counter_begin(ctx)) != P252_OK) return rc;
+        cudaError_t le = p252::launch_merkle_verify(limbs(&tag), limbs(root), leaf_items, leaf_idx, paths, n, arity,
+                                                    (uint32_t)depth, ok, n_failed ? ctx->d_counter : nullptr, ctx->stream);
+        if (le != cudaSuccess) return fail_cuda(ctx, le, "kernel launch");
+        ctx->launches++;
+        if ((rc = counter_end(ctx, n_failed)) != P252_OK) return rc;
+        if (!(flags & P252_ASYNC)) CU(cudaStreamSynchronize(ctx->stream));
+        return P252_OK;
+    }
+    const size_t path_bytes = (size_t)depth * (size_t)arity * 32;
+    std::vector<Io> ios = {{leaf_items, nullptr, 32}, {leaf_idx, nullptr, 8}, {paths, nullptr, path_bytes}, {nullptr, ok, 1}};
+    rc = run_host_pipeline(ctx, ios, n, [&](void** d, size_t cnt, cudaStream_t st) {
+        return p252::launch_merkle_verify(limbs(&tag), limbs(root), d[0], static_cast<const uint64_t*>(d[1]), d[2], cnt, arity,
+                                          (uint32_t)depth, static_cast<uint8_t*>(d[3]), nullptr, st);
+    });
+    if (rc == P252_OK && n_failed) {
+        size_t bad = 0;
+        for (size_t i = 0; i < n; ++i) bad += ok[i] ? 0 : 1;
+        *n_failed = bad;
+    }
+    return rc;
+}
+
 // ---- multi-GPU ------------------------------------------------------------------------------------------
 int p252_dist_unique_id(uint8_t id[P252_NCCL_UNIQUE_ID_BYTES]) {
     static_assert(sizeof(ncclUniqueId) <= P252_NCCL_UNIQUE_ID_BYTES, "unique id size");
@@ -656,6 +873,7 @@ int p252_dist_unique_id(uint8_t id[P252_NCCL_UNIQUE_ID_BYTES]) {
 int p252_dist_init(p252_ctx* ctx, const uint8_t id[P252_NCCL_UNIQUE_ID_BYTES], int rank, int nranks) {
     if (!ctx || !id || nranks < 1 || rank < 0 || rank >= nranks) return P252_ERR_INVALID_ARGUMENT;
     if (ctx->comm) return P252_ERR_INVALID_ARGUMENT;
+    P252_LOCK(ctx);
     DeviceGuard g(ctx->device);
     if (!nccl().ok) return fail_nccl(ctx, ncclSystemError, "dlopen(libnccl.so.2)");
     ncclUniqueId u;
@@ -669,6 +887,7 @@ int p252_dist_init(p252_ctx* ctx, const uint8_t id[P252_NCCL_UNIQUE_ID_BYTES], i
 
 int p252_dist_finalize(p252_ctx* ctx) {
     if (!ctx) return P252_ERR_INVALID_ARGUMENT;
+    P252_LOCK(ctx);
     DeviceGuard g(ctx->device);
     if (ctx->comm) {
         CU(cudaStreamSynchronize(ctx->comm_stream));
@@ -724,9 +943,24 @@ int p252_merkle4_build_dist(p252_ctx* ctx, const p252_fr* leaves_shard, size_t n
     int lv = 0;
     int rc = p252_merkle4_shard_plan(n_leaves_total, G, r, plan, 64, &lv);
     if (rc != P252_OK) return rc;
+    P252_LOCK(ctx);
     DeviceGuard g(ctx->device);
     p252_fr tag;
     p252_hash_tag(P252_DOMAIN_MERKLE4, 4, 1, &tag);
+
+    const bool timing = (flags & P252_TIMING) != 0;
+    const bool no_gather = (flags & P252_NO_GATHER) != 0;
+    if (timing) {
+        // events with timing enabled, created once per context and reused
+        while ((int)ctx->level_events.size() < lv) {
+            p252_ctx::LevelEvents le;
+            for (cudaEvent_t* ev : {&le.k0, &le.k1, &le.g0, &le.g1}) CU(cudaEventCreate(ev));
+            ctx->level_events.push_back(le);
+        }
+        ctx->level_info.assign((size_t)lv, p252_level_timing{});
+        ctx->level_gathered.assign((size_t)lv, 0);
+    }
+    ctx->timed_levels = timing ? lv : 0;
 
     const p252_fr* below_full = nullptr;        // complete level below (valid once gathered)
     const p252_fr* below_mine = leaves_shard;   // this rank's slice of the level below
@@ -735,15 +969,27 @@ int p252_merkle4_build_dist(p252_ctx* ctx, const p252_fr* leaves_shard, size_t n
     for (int l = 0; l < lv; ++l) {
         const p252_level_plan& p = plan[l];
         p252_fr* level = nodes_out + p.level_offset;
+        if (timing) {
+            ctx->level_info[(size_t)l].nodes = p.level_size;
+            ctx->level_info[(size_t)l].my_nodes = p.my_count;
+        }
         if (p.sharded) {
             // the first level is always sharded (n_leaves_total / G is a multiple of 4)
+            if (timing) CU(cudaEventRecord(ctx->level_events[(size_t)l].k0, ctx->stream));
             cudaError_t le = p252::launch_digest(limbs(&tag), below_mine, p.my_count, 4, level + p.my_offset, 1, false, ctx->stream);
             if (le != cudaSuccess) return fail_cuda(ctx, le, "kernel launch");
             ctx->launches++;
-            if (G > 1) {
+            if (timing) CU(cudaEventRecord(ctx->level_events[(size_t)l].k1, ctx->stream));
+            if (G > 1 && !no_gather) {
                 CU(cudaEventRecord(ctx->ev_level, ctx->stream));
                 CU(cudaStreamWaitEvent(ctx->comm_stream, ctx->ev_level, 0));
+                if (timing) CU(cudaEventRecord(ctx->level_events[(size_t)l].g0, ctx->comm_stream));
                 NC(nccl().AllGather(level + p.my_offset, level, p.my_count * 4, ncclUint64, ctx->comm, ctx->comm_stream));
+                if (timing) {
+                    CU(cudaEventRecord(ctx->level_events[(size_t)l].g1, ctx->comm_stream));
+                    ctx->level_gathered[(size_t)l] = 1;
+                    ctx->level_info[(size_t)l].gather_bytes = p.level_size * sizeof(p252_fr);
+                }
                 CU(cudaEventRecord(ctx->ev_comm, ctx->comm_stream));
                 gather_in_flight = true;
             }
@@ -753,15 +999,41 @@ int p252_merkle4_build_dist(p252_ctx* ctx, const p252_fr* leaves_shard, size_t n
                 CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_comm, 0));
                 gather_in_flight = false;
             }
+            if (timing) CU(cudaEventRecord(ctx->level_events[(size_t)l].k0, ctx->stream));
             cudaError_t le = p252::launch_digest(limbs(&tag), below_full, p.level_size, 4, level, 1, false, ctx->stream);
             if (le != cudaSuccess) return fail_cuda(ctx, le, "kernel launch");
             ctx->launches++;
+            if (timing) CU(cudaEventRecord(ctx->level_events[(size_t)l].k1, ctx->stream));
         }
         below_full = level;
     }
     // every level must be complete on every rank before the call is considered done
     CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_comm, 0));
+    if (timing) CU(cudaEventRecord(ctx->ev_tree_end, ctx->stream));
     if (!(flags & P252_ASYNC)) CU(cudaStreamSynchronize(ctx->stream));
+    return P252_OK;
+}
+
+int p252_tree_level_timings(p252_ctx* ctx, p252_level_timing* levels, int capacity, int* n_levels, float* total_ms) {
+    if (!ctx) return P252_ERR_INVALID_ARGUMENT;
+    P252_LOCK(ctx);
+    DeviceGuard g(ctx->device);
+    const int lv = ctx->timed_levels;
+    if (n_levels) *n_levels = lv;
+    if (lv == 0) return P252_ERR_INVALID_ARGUMENT;   // no P252_TIMING build on this context yet
+    CU(cudaStreamSynchronize(ctx->stream));
+    if (ctx->comm_stream) CU(cudaStreamSynchronize(ctx->comm_stream));
+    if (total_ms) CU(cudaEventElapsedTime(total_ms, ctx->level_events[0].k0, ctx->ev_tree_end));
+    if (!levels) return P252_OK;
+    if (capacity < lv) return P252_ERR_INVALID_ARGUMENT;
+    for (int l = 0; l < lv; ++l) {
+        p252_level_timing t = ctx->level_info[(size_t)l];
+        CU(cudaEventElapsedTime(&t.kernel_ms, ctx->level_events[(size_t)l].k0, ctx->level_events[(size_t)l].k1));
+        t.gather_ms = 0.f;
+        if (ctx->level_gathered[(size_t)l])
+            CU(cudaEventElapsedTime(&t.gather_ms, ctx->level_events[(size_t)l].g0, ctx->level_events[(size_t)l].g1));
+        levels[l] = t;
+    }
     return P252_OK;
 }
 

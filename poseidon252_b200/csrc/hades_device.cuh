@@ -75,6 +75,16 @@ constexpr int kRounds = 68;
 constexpr int kHalfFull = 4;
 constexpr int kPartial = 60;
 
+// Work per permutation in this formulation (see hades_permute below): 100 S-boxes (5 per full round, 1 per partial
+// round) = 200 squarings + 100 products, 60 lane-4 corrections, 5 final products; 68 mixes of 5 Montgomery rows.
+constexpr int kSboxPerPerm = 2 * kHalfFull * 5 + kPartial;
+constexpr int kMontSqrPerPerm = 2 * kSboxPerPerm;
+constexpr int kMontMulPerPerm = kSboxPerPerm + kPartial + 5;
+constexpr int kWideMulPerPerm = kMontSqrPerPerm * (kWideOps_fr_sqr_wide + kWideOps_fr_redc_wide) +
+                                kMontMulPerPerm * (kWideOps_fr_row_first + 7 * kWideOps_fr_row) +
+                                kRounds * 5 * kWideOps_fr_arc_redc1;
+constexpr int kDfmaPerPerm = kRounds * 5 * 5 * 8;
+
 // r = (x*y + m p) / 2^256.  Row operand x must satisfy x + p <= 2^256; y < 2^256.
 __device__ __forceinline__ void montmul(uint32_t (&r)[8], const uint32_t (&x)[8],
                                         const uint32_t (&y)[8]) {

@@ -214,7 +214,7 @@ template <bool kDecrypt>
 __global__ void __launch_bounds__(kThreads, kMinBlocks) k_crypt(FrArg tag, const uint8_t* __restrict__ src, size_t n, uint32_t L,
                                                     const uint8_t* __restrict__ secret_uv,
                                                     const uint8_t* __restrict__ nonce, uint8_t* dst,
-                                                    uint8_t* __restrict__ ok) {
+                                                    uint8_t* __restrict__ ok, unsigned long long* __restrict__ n_failed) {
     P252_STAGE_TABLES
     const size_t i = (size_t)blockIdx.x * kThreads + threadIdx.x;
     if (i >= n) return;
@@ -290,6 +290,107 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) k_crypt(FrArg tag, const
             const uint32_t zero[8] = {0, 0, 0, 0, 0, 0, 0, 0};
             for (uint32_t k = 0; k < L; ++k) store_fr(dsti + (size_t)k * 32, zero);
         }
+        if (n_failed) {                                   // one atomic per warp that saw a failure
+            const unsigned act = __activemask();
+            const unsigned bad = __ballot_sync(act, !good);
+            if (bad && (threadIdx.x & 31) == (unsigned)(__ffs(act) - 1)) atomicAdd(n_failed, (unsigned long long)__popc(bad));
+        }
+    }
+}
+
+// ---- Merkle openings (consumer: poseidon-merkle `Opening`, /root/reference/AGENTS.md:62-66) -------------------
+// A tree over n_leaves = arity^depth leaves is stored as `leaves` + `nodes` (internal levels bottom-up, root last:
+// the layout p252_merkle_build writes).  The opening of leaf i holds, for every level l = 0..depth-1 (0 = leaf level),
+// the whole sibling group of the path node: the `arity` items at positions [g*arity, (g+1)*arity) of level l, with
+// g = i / arity^(l+1); the path node itself sits at offset (i / arity^l) % arity inside its group.
+// k_merkle_open: pure gather, one thread per (opening, level).
+__global__ void __launch_bounds__(256) k_merkle_open(const uint8_t* __restrict__ leaves, const uint8_t* __restrict__ nodes,
+                                                     const uint64_t* __restrict__ leaf_idx, size_t n, uint32_t log2_arity,
+                                                     uint32_t depth, uint64_t n_leaves, uint8_t* __restrict__ paths) {
+    const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n * depth) return;
+    const size_t item = t / depth;
+    const uint32_t level = (uint32_t)(t % depth);
+    const uint32_t arity = 1u << log2_arity;
+    uint64_t idx = leaf_idx[item];
+    if (idx >= n_leaves) idx = 0;                         // rejected on the host for HOST buffers; clamp for device ones
+    const uint64_t group = idx >> (log2_arity * (level + 1));
+    const uint8_t* src;
+    if (level == 0) {
+        src = leaves + group * arity * 32;
+    } else {
+        // offset of internal level (level-1): sum_{q<level-1} n_leaves / arity^(q+1)
+        uint64_t off = 0, m = n_leaves >> log2_arity;
+        for (uint32_t q = 0; q + 1 < level; ++q, m >>= log2_arity) off += m;
+        src = nodes + (off + group * arity) * 32;
+    }
+    uint8_t* dst = paths + ((size_t)item * depth + level) * arity * 32;
+    for (uint32_t q = 0; q < arity * 2; ++q)
+        reinterpret_cast<uint4*>(dst)[q] = ldg128(src + q * 16);
+}
+
+// k_merkle_verify: one thread per opening, `depth` chained Merkle digests (Hash::digest(Domain::MerkleA, group),
+// /root/reference/src/hash.rs:22-31,191-195) with the membership check of every level fused in:
+//   cur = leaf;  for l: require group[l][pos_l] == cur;  cur = digest(group[l]);   finally require cur == root.
+// The sibling groups are read with the same warp-cooperative 128-bit tile as k_sponge_digest.
+template <int kLog2Arity>
+__global__ void __launch_bounds__(kThreads, kMinBlocks) k_merkle_verify(FrArg tag, FrArg root, const uint8_t* __restrict__ leaf_items,
+                                                                        const uint64_t* __restrict__ leaf_idx,
+                                                                        const uint8_t* __restrict__ paths, size_t n, uint32_t depth,
+                                                                        uint8_t* __restrict__ ok,
+                                                                        unsigned long long* __restrict__ n_failed) {
+    constexpr int kArity = 1 << kLog2Arity;
+    __shared__ uint4 stage[kWarps][32][8];
+    P252_STAGE_TABLES
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const size_t item0 = ((size_t)blockIdx.x * kWarps + warp) * 32;
+    if (item0 >= n) return;
+    const int nitems = (n - item0 < 32) ? (int)(n - item0) : 32;
+    const bool live = lane < nitems;
+    uint4(*st)[8] = stage[warp];
+    const size_t me = item0 + (live ? lane : 0);
+
+    uint32_t cur[8];
+    load_fr(cur, leaf_items + me * 32);
+    uint64_t idx = leaf_idx[me];
+    bool good = true;
+    const size_t stride = (size_t)depth * kArity * 32;
+    const uint8_t* base = paths + item0 * stride;
+#pragma unroll 1
+    for (uint32_t level = 0; level < depth; ++level) {
+        uint32_t v[4][8];
+        warp_gather(st, base + (size_t)level * kArity * 32, stride, nitems, kArity, lane, v);
+        const uint32_t pos = (uint32_t)idx & (kArity - 1);
+        idx >>= kLog2Arity;
+        uint32_t diff = 0;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            uint32_t sel = v[0][k];
+#pragma unroll
+            for (int q = 1; q < kArity; ++q) sel = (pos == (uint32_t)q) ? v[q][k] : sel;
+            diff |= sel ^ cur[k];
+        }
+        good = good && (diff == 0);
+        uint32_t s[5][8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            s[0][k] = tag.l[k];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) s[1 + q][k] = (q < kArity) ? v[q][k] : 0u;
+        }
+        hades_permute(s P252_TAB_PASS);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) cur[k] = s[1][k];
+    }
+    uint32_t diff = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) diff |= cur[k] ^ root.l[k];
+    good = good && (diff == 0) && (idx == 0);             // idx != 0: leaf index beyond arity^depth
+    if (live) ok[me] = good ? 1 : 0;
+    if (n_failed) {
+        const unsigned bad = __ballot_sync(0xffffffffu, live && !good);
+        if (bad && lane == 0) atomicAdd(n_failed, (unsigned long long)__popc(bad));
     }
 }
 
@@ -366,18 +467,50 @@ cudaError_t launch_encrypt(const uint64_t tag[4], const void* msg, size_t n, uin
     k_crypt<false><<<grid_for(n), kThreads, 0, st>>>(to_arg(tag), static_cast<const uint8_t*>(msg), n, L,
                                                      static_cast<const uint8_t*>(secret_uv),
                                                      static_cast<const uint8_t*>(nonce),
-                                                     static_cast<uint8_t*>(cipher), nullptr);
+                                                     static_cast<uint8_t*>(cipher), nullptr, nullptr);
     return cudaGetLastError();
 }
 
 cudaError_t launch_decrypt(const uint64_t tag[4], const void* cipher, size_t n, uint32_t L, const void* secret_uv,
-                           const void* nonce, void* msg, uint8_t* ok, cudaStream_t st) {
+                           const void* nonce, void* msg, uint8_t* ok, unsigned long long* n_failed, cudaStream_t st) {
     if (n == 0) return cudaSuccess;
     k_crypt<true><<<grid_for(n), kThreads, 0, st>>>(to_arg(tag), static_cast<const uint8_t*>(cipher), n, L,
                                                     static_cast<const uint8_t*>(secret_uv),
                                                     static_cast<const uint8_t*>(nonce), static_cast<uint8_t*>(msg),
-                                                    ok);
+                                                    ok, n_failed);
     return cudaGetLastError();
+}
+
+cudaError_t launch_merkle_open(const void* leaves, const void* nodes, const uint64_t* leaf_idx, size_t n, int arity,
+                               uint32_t depth, uint64_t n_leaves, void* paths, cudaStream_t st) {
+    if (n == 0 || depth == 0) return cudaSuccess;
+    const size_t total = n * depth;
+    k_merkle_open<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(static_cast<const uint8_t*>(leaves),
+                                                                   static_cast<const uint8_t*>(nodes), leaf_idx, n,
+                                                                   arity == 4 ? 2u : 1u, depth, n_leaves,
+                                                                   static_cast<uint8_t*>(paths));
+    return cudaGetLastError();
+}
+
+cudaError_t launch_merkle_verify(const uint64_t tag[4], const uint64_t root[4], const void* leaf_items,
+                                 const uint64_t* leaf_idx, const void* paths, size_t n, int arity, uint32_t depth,
+                                 uint8_t* ok, unsigned long long* n_failed, cudaStream_t st) {
+    if (n == 0) return cudaSuccess;
+    if (arity == 4)
+        k_merkle_verify<2><<<grid_for(n), kThreads, 0, st>>>(to_arg(tag), to_arg(root), static_cast<const uint8_t*>(leaf_items),
+                                                             leaf_idx, static_cast<const uint8_t*>(paths), n, depth, ok, n_failed);
+    else
+        k_merkle_verify<1><<<grid_for(n), kThreads, 0, st>>>(to_arg(tag), to_arg(root), static_cast<const uint8_t*>(leaf_items),
+                                                             leaf_idx, static_cast<const uint8_t*>(paths), n, depth, ok, n_failed);
+    return cudaGetLastError();
+}
+
+uint32_t wide_mul_per_permutation() { return (uint32_t)kWideMulPerPerm; }
+uint32_t dfma_per_permutation() { return (uint32_t)kDfmaPerPerm; }
+
+void kernel_launch_shape(int* threads_per_block, int* min_blocks_per_sm) {
+    *threads_per_block = kThreads;
+    *min_blocks_per_sm = kMinBlocks;
 }
 
 }  // namespace p252

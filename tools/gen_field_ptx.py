@@ -27,6 +27,7 @@ assert PL[0] == 1 and PL[1] == M32
 # p1 = 2^32 - 1: m*p1 = (m << 32) - m, i.e. lo = -m = w0 (the limb being cancelled) and hi = m - (m != 0).
 # With P1_ALU the two halves are formed on the ALU pipe (borrow of 0 - w0) instead of an IMAD.HI.
 P1_ALU = os.environ.get("P252_P1_ALU", "0") == "1"
+FUSE_FRESH = os.environ.get("P252_FUSE_FRESH", "1") == "1"
 
 Operand = Union[str, int]
 
@@ -89,6 +90,11 @@ class Prog:
                 continue
             if base == "mov":
                 reg[d] = val(src[0])
+                continue
+            if base == "mulwide":       # (lo|hi) = a * b as ONE 64-bit product (mul.wide.u32 + mov.b64 unpack)
+                lo, hi = d.split("|")
+                prod = val(src[0]) * val(src[1])
+                reg[lo], reg[hi] = prod & M32, prod >> 32
                 continue
             if base == "and":
                 reg[d] = val(src[0]) & val(src[1])
@@ -158,9 +164,19 @@ class Prog:
             lines.append(".reg .u32 %s;" % ", ".join(self.temps))
         if self.preds:
             lines.append(".reg .pred %s;" % ", ".join(self.preds))
+        n64 = 0
         for opc, d, src, _nc, guard in self.ops:
             g = "@%s " % guard if guard else ""
+            if opc == "mulwide":
+                lo, hi = d.split("|")
+                w = "wd%d" % n64
+                n64 += 1
+                lines.append("mul.wide.u32 %s, %s, %s;" % (w, fmt(src[0]), fmt(src[1])))
+                lines.append("mov.b64 {%s, %s}, %s;" % (fmt(lo), fmt(hi), w))
+                continue
             lines.append("%s%s %s;" % (g, opc, ", ".join([fmt(d)] + [fmt(s) for s in src])))
+        if n64:
+            lines.insert(0, ".reg .u64 %s;" % ", ".join("wd%d" % i for i in range(n64)))
         body = "\n".join('        "%s\\n\\t"' % ln for ln in ["{"] + lines + ["}"])
         cons_out = ", ".join(['"=&r"(%s)' % n for n in self.outs] + ['"+r"(%s)' % n for n in self.inouts])
         cons_in = ", ".join('"r"(%s)' % n for n in self.ins)
@@ -293,8 +309,12 @@ def gen_redc1(with_arc: bool) -> Prog:
     o = pg.tmp(*["o%d" % k for k in range(1, 9)])     # o[k-1] <-> limb k
     pg.op("sub.u32", m, 0, t[0])
     for idx, pj in enumerate((1, 3, 5, 7)):           # odd columns (1,2),(3,4),(5,6),(7,8): fresh
-        pg.op("mul.lo.u32", o[2 * idx], m, PL[pj])
-        pg.op("mul.hi.u32", o[2 * idx + 1], m, PL[pj])
+        if FUSE_FRESH and pj != 1:
+            # one 64-bit product: ONE IMAD.WIDE.U32 instead of the IMAD + IMAD.HI pair ptxas makes of mul.lo / mul.hi
+            pg.op("mulwide", o[2 * idx] + "|" + o[2 * idx + 1], m, PL[pj])
+        else:
+            pg.op("mul.lo.u32", o[2 * idx], m, PL[pj])
+            pg.op("mul.hi.u32", o[2 * idx + 1], m, PL[pj])
     pg.op("add.cc.u32", t[0], t[0], m)                # limb 0 cancels; carry = (t0 != 0)
     pg.op("addc.cc.u32", t[1], t[1], 0)
     for k in (2, 4, 6):                               # even columns (2,3),(4,5),(6,7)
@@ -502,6 +522,10 @@ def gen_redc_wide() -> Prog:
         # odd columns += m * (p1, p3, p5, p7)
         for idx, k in enumerate(odd_cols):
             pj = PL[k + 1]
+            if FUSE_FRESH and OD[k] is None and OD[k + 1] is None and not cf and k + 1 != 7:
+                OD[k], OD[k + 1] = fresh("w"), fresh("w")
+                pg.op("mulwide", OD[k] + "|" + OD[k + 1], m, pj)     # one IMAD.WIDE.U32 (see gen_redc1)
+                continue
             for half, kk in (("lo", k), ("hi", k + 1)):
                 last = (kk == 7)
                 if OD[kk] is not None or cf:
@@ -638,8 +662,19 @@ namespace p252 {
 '''
 
 
+def wide_ops(pg: Prog) -> int:
+    """32x32->64-bit multiplier instructions a primitive issues: every *.hi half (its .lo partner fuses into the same
+    IMAD.WIDE; a lone .hi is an IMAD.HI) and every mul.wide."""
+    return sum(1 for opc, *_ in pg.ops if opc == "mulwide" or ".hi" in opc)
+
+
 def emit_header() -> str:
     s = HEADER
+    s += "// multiplier instructions (IMAD.WIDE / IMAD.HI class) per primitive, counted by the generator\n"
+    for pg in ALL:
+        if wide_ops(pg):
+            s += "constexpr int kWideOps_%s = %d;\n" % (pg.name, wide_ops(pg))
+    s += "\n"
     for pg in ALL:
         s += "// %s\n" % pg.doc
         s += "__device__ __forceinline__ void %s(%s) {\n" % (pg.name, SIGS[pg.name])
