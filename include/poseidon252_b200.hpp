@@ -199,4 +199,66 @@ inline std::vector<Scalar> merkle4_build(const std::vector<Scalar>& leaves, Engi
     return nodes;
 }
 
+// Tree of Domain::Merkle2 / Merkle4 digests for arity 2 / 4 (src/hash.rs:22-31), internal levels bottom-up
+inline std::vector<Scalar> merkle_build(int arity, const std::vector<Scalar>& leaves, Engine& e = Engine::default_engine()) {
+    size_t n_internal = 0;
+    check(p252_merkle_tree_nodes(arity, leaves.size(), &n_internal, nullptr));
+    std::vector<Scalar> nodes(n_internal);
+    check(p252_merkle_build(e.get(), arity, leaves.data(), leaves.size(), nodes.data(), P252_MEM_HOST), e.get());
+    return nodes;
+}
+
+// Mirror of poseidon-merkle's `Opening<T, H, A>` (consumer crate, AGENTS.md:62-66): the root, for every level
+// (0 = leaf level) the whole sibling group of the path node, and the node's offset inside the group.
+struct Opening {
+    int arity = 4;
+    Scalar root{};
+    std::vector<Scalar> branch;       // depth x arity
+    std::vector<size_t> positions;    // depth
+    uint64_t leaf_index = 0;
+    size_t depth() const { return positions.size(); }
+    // Opening::verify(item): depth chained Merkle digests + membership checks, on the device
+    bool verify(const Scalar& item, Engine& e = Engine::default_engine()) const {
+        uint8_t ok = 0;
+        check(p252_merkle_verify_batch(e.get(), arity, static_cast<int>(depth()), &item, &leaf_index, branch.data(), &root,
+                                       1, &ok, nullptr, P252_MEM_HOST),
+              e.get());
+        return ok != 0;
+    }
+};
+
+// Openings of the leaves `leaf_idx` of a tree held as leaves + nodes (merkle_build layout)
+inline std::vector<Opening> merkle_open_batch(int arity, const std::vector<Scalar>& leaves, const std::vector<Scalar>& nodes,
+                                              const std::vector<uint64_t>& leaf_idx, Engine& e = Engine::default_engine()) {
+    int depth = 0;
+    size_t n_internal = 0;
+    check(p252_merkle_tree_nodes(arity, leaves.size(), &n_internal, &depth));
+    if (nodes.size() != n_internal) throw Error(P252_ERR_INVALID_ARGUMENT, "node array does not match the leaf count");
+    std::vector<Scalar> paths(leaf_idx.size() * depth * arity);
+    check(p252_merkle_open_batch(e.get(), arity, leaves.data(), leaves.size(), nodes.data(), leaf_idx.data(), leaf_idx.size(),
+                                 paths.data(), P252_MEM_HOST),
+          e.get());
+    std::vector<Opening> out(leaf_idx.size());
+    for (size_t i = 0; i < out.size(); ++i) {
+        Opening& o = out[i];
+        o.arity = arity;
+        o.root = nodes.back();
+        o.leaf_index = leaf_idx[i];
+        o.branch.assign(paths.begin() + i * depth * arity, paths.begin() + (i + 1) * depth * arity);
+        uint64_t idx = leaf_idx[i];
+        for (int l = 0; l < depth; ++l, idx /= static_cast<uint64_t>(arity)) o.positions.push_back(idx % arity);
+    }
+    return out;
+}
+
+// n x Opening::verify with all openings in one launch: ok[i] != 0 iff paths[i] proves items[i] under root
+inline std::vector<uint8_t> merkle_verify_batch(int arity, int depth, const Scalar* items, const uint64_t* leaf_idx,
+                                                const Scalar* paths, const Scalar& root, size_t n,
+                                                Engine& e = Engine::default_engine()) {
+    std::vector<uint8_t> ok(n);
+    check(p252_merkle_verify_batch(e.get(), arity, depth, items, leaf_idx, paths, &root, n, ok.data(), nullptr, P252_MEM_HOST),
+          e.get());
+    return ok;
+}
+
 }  // namespace p252

@@ -56,6 +56,18 @@ int main() {
     } catch (const Error& e) {
         if (!e.is_decryption_failed()) return 11;
     }
+    // Merkle tree + openings (arity 4 and 2): every opening verifies, a wrong item or a tampered sibling does not
+    for (int arity : {4, 2}) {
+        std::vector<Scalar> leaves(64);
+        for (size_t i = 0; i < leaves.size(); ++i) leaves[i] = Scalar{{100 + i, i, 0, 0}};
+        auto nodes = merkle_build(arity, leaves);
+        auto ops = merkle_open_batch(arity, leaves, nodes, {0, 7, 63});
+        if (ops.size() != 3 || ops[1].depth() != (arity == 4 ? 3u : 6u)) return 12;
+        if (!ops[1].verify(leaves[7]) || ops[1].verify(leaves[8])) return 13;
+        Opening bad = ops[2];
+        bad.branch[1].l[1] ^= 4;
+        if (!ops[2].verify(leaves[63]) || bad.verify(leaves[63])) return 14;
+    }
     std::puts("host mirror ok (GPU)");
     return 0;
 }

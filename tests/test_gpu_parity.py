@@ -129,14 +129,28 @@ def test_merkle_domains_batch(engine, oracle, coracle):
 
 
 def test_sweep_lengths(engine, oracle, coracle):
-    """config 5 shape at reduced batch: Domain::Other, in_len 1..256 (every length up to 40, then sparse)."""
+    """config 5 shape at reduced batch: Domain::Other, EVERY in_len 1..256 (ragged 40-item batches: partial warps
+    and, for in_len % 4 != 0, partial tile loads)."""
+    import os
     rng = np.random.default_rng(5)
-    for in_len in list(range(1, 41)) + [63, 64, 65, 127, 128, 200, 255, 256]:
+    th = min(8, os.cpu_count() or 1)
+    for in_len in range(1, 257):
         n = 40
         data = random_limbs_fast(rng, (n, in_len))
         got = pb.Hash.digest_batch(pb.Domain.Other, data, engine=engine)
         tag = _tag(oracle, [oracle.Absorb(in_len), oracle.Squeeze(1)], oracle.Domain.Other)
-        assert np.array_equal(got, coracle.digest(tag, data, in_len, 1)), in_len
+        assert np.array_equal(got, coracle.digest(tag, data, in_len, 1, threads=th)), in_len
+
+
+@pytest.mark.parametrize("in_len", [1, 4, 5, 255, 256])
+def test_sweep_lengths_4096_items(engine, oracle, coracle, in_len):
+    """the sweep's corner lengths on a 2^12-item batch (several blocks per SM, full and partial last chunks)"""
+    import os
+    rng = np.random.default_rng(50 + in_len)
+    data = random_limbs_fast(rng, (1 << 12, in_len))
+    got = pb.Hash.digest_batch(pb.Domain.Other, data, engine=engine)
+    tag = _tag(oracle, [oracle.Absorb(in_len), oracle.Squeeze(1)], oracle.Domain.Other)
+    assert np.array_equal(got, coracle.digest(tag, data, in_len, 1, threads=min(8, os.cpu_count() or 1)))
 
 
 # ---- encryption --------------------------------------------------------------------------------------
