@@ -112,6 +112,12 @@ typedef struct p252_kernel_info {
 } p252_kernel_info;
 int p252_get_kernel_info(p252_kernel_info* out);
 
+/* Digest batches of at most `max_items` items run the lane-split kernel (five threads per sponge state: lower latency,
+ * ~3x lower throughput per state) -- the regime of single digests and of the top levels of a Merkle tree.  Default
+ * 4096 (environment variable P252_COOP_MAX overrides it at context creation); 0 disables the lane-split path.  Both
+ * kernels produce bit-identical results. */
+int p252_set_small_batch_max(p252_ctx* ctx, size_t max_items);
+
 /* Fault injection / inspection for tests (no effect unless called).  p252_debug_fail_chunk: the k-th staged chunk
  * (0-based) of the NEXT host-buffer call on this context fails as if its kernel launch had failed (one shot).
  * p252_debug_staging_nonzero: number of non-zero bytes currently held by the context's staging arenas. */

@@ -44,6 +44,7 @@ SIGNATURES = {
     "p252_merkle_tree_nodes": (c_int, [c_int, c_size_t, ctypes.POINTER(c_size_t), ctypes.POINTER(c_int)]),
     "p252_merkle_build": (c_int, [c_void_p, c_int, c_void_p, c_size_t, c_void_p, c_int]),
     "p252_get_kernel_info": (c_int, [c_void_p]),
+    "p252_set_small_batch_max": (c_int, [c_void_p, c_size_t]),
     "p252_debug_fail_chunk": (c_int, [c_void_p, ctypes.c_longlong]),
     "p252_debug_staging_nonzero": (c_int, [c_void_p, ctypes.POINTER(c_size_t)]),
     "p252_merkle_open_batch": (c_int, [c_void_p, c_int, c_void_p, c_size_t, c_void_p, c_void_p, c_size_t, c_void_p, c_int]),

@@ -50,6 +50,7 @@ struct p252_ctx {
     // device-side failure counter (decrypt / opening verification on DEVICE buffers) + its pinned mirror
     unsigned long long* d_counter = nullptr;
     unsigned long long* h_counter = nullptr;
+    size_t coop_max = 0;          // small-batch threshold of the lane-split digest kernel
     // test hook: index of the staged chunk that fails in the next host-buffer call (-1 = none)
     long long fail_chunk = -1;
     // multi-GPU
@@ -326,6 +327,7 @@ int p252_create_on_stream(int device, void* cuda_stream, p252_ctx** out) {
     if (prop.major != 10) return P252_ERR_NO_DEVICE;   // kernels are sm_100a SASS only
     p252_ctx* ctx = new p252_ctx();
     ctx->device = device;
+    ctx->coop_max = p252::coop_max_items();
     DeviceGuard g(device);
     auto bail = [&](cudaError_t e, const char* w) {
         int rc = fail_cuda(nullptr, e, w);
@@ -410,6 +412,13 @@ int p252_get_kernel_info(p252_kernel_info* out) {
     out->montmul_per_permutation = 365;
     out->threads_per_block = (uint32_t)t;
     out->min_blocks_per_sm = (uint32_t)b;
+    return P252_OK;
+}
+
+int p252_set_small_batch_max(p252_ctx* ctx, size_t max_items) {
+    if (!ctx) return P252_ERR_INVALID_ARGUMENT;
+    P252_LOCK(ctx);
+    ctx->coop_max = max_items;
     return P252_OK;
 }
 
@@ -561,11 +570,11 @@ static int digest_impl(p252_ctx* ctx, const p252_fr* tag, const p252_fr* in, siz
     if (flags & P252_MEM_DEVICE) {
         if (!aligned16(in) || !aligned16(out)) return P252_ERR_INVALID_ARGUMENT;
         if (n == 0) return P252_OK;
-        return finish_device_call(ctx, p252::launch_digest(limbs(tag), in, n, il, out, ol, truncate, ctx->stream), flags);
+        return finish_device_call(ctx, p252::launch_digest(limbs(tag), in, n, il, out, ol, truncate, ctx->coop_max, ctx->stream), flags);
     }
     std::vector<Io> ios = {{in, nullptr, in_len * 32}, {nullptr, out, out_len * 32}};
     return run_host_pipeline(ctx, ios, n, [&](void** d, size_t cnt, cudaStream_t st) {
-        return p252::launch_digest(limbs(tag), d[0], cnt, il, d[1], ol, truncate, st);
+        return p252::launch_digest(limbs(tag), d[0], cnt, il, d[1], ol, truncate, ctx->coop_max, st);
     });
 }
 
@@ -711,7 +720,7 @@ static int merkle_build_device(p252_ctx* ctx, int arity, const p252_fr* leaves, 
     const p252_fr* src = leaves;
     p252_fr* dst = nodes;
     for (size_t m = n_leaves / arity; m >= 1; m /= arity) {
-        cudaError_t le = p252::launch_digest(limbs(&tag), src, m, (uint32_t)arity, dst, 1, false, ctx->stream);
+        cudaError_t le = p252::launch_digest(limbs(&tag), src, m, (uint32_t)arity, dst, 1, false, ctx->coop_max, ctx->stream);
         if (le != cudaSuccess) return fail_cuda(ctx, le, "kernel launch");
         ctx->launches++;
         src = dst;
@@ -746,7 +755,7 @@ int p252_merkle_build(p252_ctx* ctx, int arity, const p252_fr* leaves, size_t n_
         std::vector<Io> ios = {{leaves, nullptr, (size_t)arity * 32}, {nullptr, nodes_out, 32}};
         size_t done = 0;   // the pipeline hands chunks in order; mirror each chunk into d_nodes as well
         rc = run_host_pipeline(ctx, ios, first, [&](void** d, size_t cnt, cudaStream_t st) {
-            cudaError_t e = p252::launch_digest(limbs(&tag), d[0], cnt, (uint32_t)arity, d[1], 1, false, st);
+            cudaError_t e = p252::launch_digest(limbs(&tag), d[0], cnt, (uint32_t)arity, d[1], 1, false, ctx->coop_max, st);
             if (e != cudaSuccess) return e;
             e = cudaMemcpyAsync(d_nodes + done, d[1], cnt * sizeof(p252_fr), cudaMemcpyDeviceToDevice, st);
             done += cnt;
@@ -976,7 +985,7 @@ int p252_merkle4_build_dist(p252_ctx* ctx, const p252_fr* leaves_shard, size_t n
         if (p.sharded) {
             // the first level is always sharded (n_leaves_total / G is a multiple of 4)
             if (timing) CU(cudaEventRecord(ctx->level_events[(size_t)l].k0, ctx->stream));
-            cudaError_t le = p252::launch_digest(limbs(&tag), below_mine, p.my_count, 4, level + p.my_offset, 1, false, ctx->stream);
+            cudaError_t le = p252::launch_digest(limbs(&tag), below_mine, p.my_count, 4, level + p.my_offset, 1, false, ctx->coop_max, ctx->stream);
             if (le != cudaSuccess) return fail_cuda(ctx, le, "kernel launch");
             ctx->launches++;
             if (timing) CU(cudaEventRecord(ctx->level_events[(size_t)l].k1, ctx->stream));
@@ -1000,7 +1009,7 @@ int p252_merkle4_build_dist(p252_ctx* ctx, const p252_fr* leaves_shard, size_t n
                 gather_in_flight = false;
             }
             if (timing) CU(cudaEventRecord(ctx->level_events[(size_t)l].k0, ctx->stream));
-            cudaError_t le = p252::launch_digest(limbs(&tag), below_full, p.level_size, 4, level, 1, false, ctx->stream);
+            cudaError_t le = p252::launch_digest(limbs(&tag), below_full, p.level_size, 4, level, 1, false, ctx->coop_max, ctx->stream);
             if (le != cudaSuccess) return fail_cuda(ctx, le, "kernel launch");
             ctx->launches++;
             if (timing) CU(cudaEventRecord(ctx->level_events[(size_t)l].k1, ctx->stream));

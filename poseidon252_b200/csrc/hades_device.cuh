@@ -224,6 +224,91 @@ __device__ __forceinline__ void hades_permute(uint32_t (&s)[5][8] P252_TAB_ARG) 
 }
 
 // ---------------------------------------------------------------------------------------------
+// Lane-split permutation for SMALL batches: five threads per state, thread `li` of a group holds lane `li`.
+//
+// One permutation on one thread is a chain of ~106 k dependent-ish instructions (0.18 ms for a lone warp on B200:
+// a single warp can issue an IMAD.WIDE only every ~6 cycles); a batch that does not fill the machine (the top
+// levels of a Merkle tree, a single Hash::digest) is bound by that latency, not by throughput.  Splitting the
+// state over five threads takes the four idle S-boxes of a full round and four of the five mix rows off the
+// critical path:  full round = 1 S-box + 1 mix row per thread (instead of 5 + 5), partial round = lane 4's
+// S-box and correction + 1 mix row (instead of + 5 rows).  The mix needs every lane's limbs: 5 x 8 warp shuffles.
+// Same integer arithmetic, same tables, same bounds as hades_permute() -> bit-identical results (tests compare the
+// two paths and the oracle).  Throughput per state is ~3x worse (6 states per warp instead of 32), so the
+// launchers use it only below kCoopMaxItems.
+//   li   : lane of the state this thread owns (0..4; the reference's S-box lane in partial rounds is 4,
+//          /root/reference/src/hades/permutation.rs:68)
+//   g0   : warp lane of the group's thread 0 (groups are 5 consecutive lanes; lanes 30,31 of a warp idle)
+//   crow : this thread's row of the small-integer MDS as doubles, crow[j] = hades_cmat(li, j)
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void coop_load_row(uint32_t (&c)[12], const uint32_t* row) {
+    const uint4 a = __ldg(reinterpret_cast<const uint4*>(row)), b = __ldg(reinterpret_cast<const uint4*>(row) + 1),
+                d = __ldg(reinterpret_cast<const uint4*>(row) + 2);
+    c[0] = a.x, c[1] = a.y, c[2] = a.z, c[3] = a.w, c[4] = b.x, c[5] = b.y, c[6] = b.z, c[7] = b.w;
+    c[8] = d.x, c[9] = d.y, c[10] = d.z, c[11] = d.w;
+}
+
+__device__ __forceinline__ void coop_mix(uint32_t (&s)[8], int next_round, int li, int g0, const double (&crow)[5]) {
+    uint32_t a12[12];
+    coop_load_row(a12, gA[next_round][li]);          // issued first: its latency hides behind the shuffles
+    uint32_t t[9];
+    uint32_t hi_prev = 0, carry = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        double acc = kTwo52;
+#pragma unroll
+        for (int j = 0; j < 5; ++j) {
+            const uint32_t z = __shfl_sync(0xffffffffu, s[k], g0 + j);
+            acc = fma(crow[j], (double)z, acc);
+        }
+        const uint64_t sum = (uint64_t)(uint32_t)__double2loint(acc) + hi_prev + carry;
+        t[k] = (uint32_t)sum;
+        carry = (uint32_t)(sum >> 32);
+        hi_prev = (uint32_t)__double2hiint(acc);
+    }
+    t[8] = hi_prev + carry;
+    uint32_t c[9];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) c[k] = a12[k];
+    fr_arc_redc1(s, t, c);
+}
+
+__device__ __forceinline__ void hades_permute_coop(uint32_t (&s)[8], int li, int g0, const double (&crow)[5]) {
+    {
+        // first add_round_constants + one full conditional subtraction, exactly as hades_permute()
+        const uint4 a = __ldg(reinterpret_cast<const uint4*>(gA0[li])), b = __ldg(reinterpret_cast<const uint4*>(gA0[li]) + 1);
+        const uint32_t c[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+        uint32_t t[8];
+        fr_add_lazy(t, s, c);
+        fr_condsub(t);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) s[k] = t[k];
+    }
+#pragma unroll 1
+    for (int r = 0; r < kRounds; ++r) {
+        const bool full = (r < kHalfFull) || (r >= kHalfFull + kPartial);
+        uint32_t w[8];
+        sbox(w, s);                                   // every thread runs it; in partial rounds only lane 4 keeps it
+        if (full) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) s[k] = w[k];
+        } else {
+            uint32_t c[8], z[8];
+            load_const(c, P252_G_ROW(r - kHalfFull));
+            montmul(z, c, w);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) s[k] = (li == 4) ? z[k] : s[k];
+        }
+        coop_mix(s, r + 1, li, g0, crow);
+    }
+    uint32_t c[8], w[8];
+    load_const(c, kF);
+    montmul(w, c, s);
+    fr_condsub(w);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) s[k] = w[k];
+}
+
+// ---------------------------------------------------------------------------------------------
 // Modular add / sub on fully reduced operands (Safe::add, Encryption::subtract,
 // /root/reference/src/hades/permutation/scalar.rs:33-35,69-75)
 // ---------------------------------------------------------------------------------------------

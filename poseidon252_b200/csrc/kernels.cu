@@ -11,6 +11,8 @@
 // pos == 4; any absorb forces a permutation before the next squeeze.
 #include "kernels.h"
 
+#include <cstdlib>
+
 #include "hades_device.cuh"
 
 namespace p252 {
@@ -85,6 +87,22 @@ __device__ __forceinline__ void warp_scatter(uint4 (*st)[8], uint8_t* base, size
     __syncwarp();
 }
 
+// ---- per-thread scalar loads / stores (2 x 128-bit) ---------------------------------------------------
+__device__ __forceinline__ void load_fr(uint32_t (&d)[8], const uint8_t* p) {
+    const uint4 a = ldg128(p), b = ldg128(p + 16);
+    d[0] = a.x, d[1] = a.y, d[2] = a.z, d[3] = a.w;
+    d[4] = b.x, d[5] = b.y, d[6] = b.z, d[7] = b.w;
+}
+__device__ __forceinline__ void load_fr_rw(uint32_t (&d)[8], const uint8_t* p) {   // coherent (own stores)
+    const uint4 a = *reinterpret_cast<const uint4*>(p), b = *reinterpret_cast<const uint4*>(p + 16);
+    d[0] = a.x, d[1] = a.y, d[2] = a.z, d[3] = a.w;
+    d[4] = b.x, d[5] = b.y, d[6] = b.z, d[7] = b.w;
+}
+__device__ __forceinline__ void store_fr(uint8_t* p, const uint32_t (&d)[8]) {
+    *reinterpret_cast<uint4*>(p) = make_uint4(d[0], d[1], d[2], d[3]);
+    *reinterpret_cast<uint4*>(p + 16) = make_uint4(d[4], d[5], d[6], d[7]);
+}
+
 // ---- Hash::digest-shaped sponge: Absorb(in_len) -> Squeeze(out_len), item-major AoS ------------
 // One permutation call site: step s > 0 is always preceded by a permutation; steps [0, nin) absorb
 // 4-scalar chunks, steps [nin, nin+nout) squeeze 4-scalar chunks.  Permutations = nin + nout - 1
@@ -151,6 +169,48 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) k_sponge_digest(FrArg ta
     }
 }
 
+// ---- the same sponge for SMALL batches: five threads per item (hades_permute_coop) ----------------------------------
+// 6 items per warp (lanes 0..29), 24 per 128-thread block.  Thread li of a group owns state lane li: lane 0 is the
+// capacity (tag), lanes 1..4 the rate, so rate thread li absorbs input scalar 4*step + li - 1 and squeezes output
+// scalar 4*c + li - 1.  Loads/stores are 2 x 128-bit per scalar per thread (tiny batches: coalescing is irrelevant).
+constexpr int kCoopItemsPerWarp = 6;
+__global__ void __launch_bounds__(kThreads) k_sponge_digest_coop(FrArg tag, const uint8_t* __restrict__ in, size_t n,
+                                                                 uint32_t in_len, uint8_t* __restrict__ out, uint32_t out_len) {
+    const int lane = threadIdx.x & 31;
+    const int grp = lane / 5, li = lane - grp * 5, g0 = grp * 5;
+    const size_t warp_global = (size_t)blockIdx.x * kWarps + (threadIdx.x >> 5);
+    const size_t item = warp_global * kCoopItemsPerWarp + grp;
+    if (warp_global * kCoopItemsPerWarp >= n) return;            // whole warp idle
+    const bool live = (grp < kCoopItemsPerWarp) && (item < n);   // idle threads still take part in the shuffles
+    double crow[5];
+#pragma unroll
+    for (int j = 0; j < 5; ++j) crow[j] = (double)(HADES_LAMBDA / (uint32_t)(li + j + 5));
+
+    uint32_t s[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) s[k] = (li == 0) ? tag.l[k] : 0u;
+    const uint32_t nin = (in_len + 3) / 4, nout = (out_len + 3) / 4;
+    const uint8_t* in_i = in + (live ? item : 0) * (size_t)in_len * 32;
+    uint8_t* out_i = out + (live ? item : 0) * (size_t)out_len * 32;
+#pragma unroll 1
+    for (uint32_t step = 0; step < nin + nout; ++step) {
+        if (step > 0) hades_permute_coop(s, li, g0, crow);
+        if (step < nin) {
+            const uint32_t q = 4 * step + (uint32_t)li - 1;      // li == 0 wraps to a huge value -> no absorb
+            if (li >= 1 && q < in_len) {
+                uint32_t v[8], t[8];
+                load_fr(v, in_i + (size_t)q * 32);
+                fr_add_mod(t, s, v);
+#pragma unroll
+                for (int k = 0; k < 8; ++k) s[k] = t[k];
+            }
+        } else {
+            const uint32_t q = 4 * (step - nin) + (uint32_t)li - 1;
+            if (live && li >= 1 && q < out_len) store_fr(out_i + (size_t)q * 32, s);
+        }
+    }
+}
+
 // ---- raw permutation of n x 5 states in place (Safe::permute) -----------------------------------
 template <bool kDense>
 __global__ void __launch_bounds__(kThreads, kDense ? 1 : kMinBlocks) k_permute(uint8_t* __restrict__ states, size_t n) {
@@ -195,21 +255,6 @@ __global__ void __launch_bounds__(kThreads, kDense ? 1 : kMinBlocks) k_permute(u
 
 // ---- encrypt / decrypt (dusk_safe::encrypt / decrypt with Domain::Encryption) -------------------
 // pattern [Absorb(2), Absorb(1), Squeeze(L), Absorb(L), Squeeze(1)]; 2*ceil(L/4) permutations.
-__device__ __forceinline__ void load_fr(uint32_t (&d)[8], const uint8_t* p) {
-    const uint4 a = ldg128(p), b = ldg128(p + 16);
-    d[0] = a.x, d[1] = a.y, d[2] = a.z, d[3] = a.w;
-    d[4] = b.x, d[5] = b.y, d[6] = b.z, d[7] = b.w;
-}
-__device__ __forceinline__ void load_fr_rw(uint32_t (&d)[8], const uint8_t* p) {   // coherent (own stores)
-    const uint4 a = *reinterpret_cast<const uint4*>(p), b = *reinterpret_cast<const uint4*>(p + 16);
-    d[0] = a.x, d[1] = a.y, d[2] = a.z, d[3] = a.w;
-    d[4] = b.x, d[5] = b.y, d[6] = b.z, d[7] = b.w;
-}
-__device__ __forceinline__ void store_fr(uint8_t* p, const uint32_t (&d)[8]) {
-    *reinterpret_cast<uint4*>(p) = make_uint4(d[0], d[1], d[2], d[3]);
-    *reinterpret_cast<uint4*>(p + 16) = make_uint4(d[4], d[5], d[6], d[7]);
-}
-
 template <bool kDecrypt>
 __global__ void __launch_bounds__(kThreads, kMinBlocks) k_crypt(FrArg tag, const uint8_t* __restrict__ src, size_t n, uint32_t L,
                                                     const uint8_t* __restrict__ secret_uv,
@@ -406,6 +451,20 @@ static inline FrArg to_arg(const uint64_t tag[4]) {
 
 static inline unsigned grid_for(size_t n) { return (unsigned)((n + kThreads - 1) / kThreads); }
 
+// Default for p252_set_small_batch_max: batches up to this many items take the lane-split kernel (latency-bound
+// regime); the environment variable P252_COOP_MAX overrides it (0 disables the lane-split path).  Measured crossover:
+// profiles/README.md "small batches".
+#ifndef P252_COOP_MAX_DEFAULT
+#define P252_COOP_MAX_DEFAULT 4096
+#endif
+size_t coop_max_items() {
+    static const size_t v = [] {
+        const char* e = getenv("P252_COOP_MAX");
+        return e ? (size_t)strtoull(e, nullptr, 10) : (size_t)P252_COOP_MAX_DEFAULT;
+    }();
+    return v;
+}
+
 cudaError_t launch_permute(void* states, size_t n, bool dense, cudaStream_t st) {
     if (n == 0) return cudaSuccess;
     if (dense)
@@ -416,8 +475,14 @@ cudaError_t launch_permute(void* states, size_t n, bool dense, cudaStream_t st) 
 }
 
 cudaError_t launch_digest(const uint64_t tag[4], const void* in, size_t n, uint32_t in_len, void* out,
-                          uint32_t out_len, bool truncate, cudaStream_t st) {
+                          uint32_t out_len, bool truncate, size_t coop_max, cudaStream_t st) {
     if (n == 0) return cudaSuccess;
+    if (!truncate && n <= coop_max) {
+        const size_t warps = (n + kCoopItemsPerWarp - 1) / kCoopItemsPerWarp;
+        k_sponge_digest_coop<<<(unsigned)((warps + kWarps - 1) / kWarps), kThreads, 0, st>>>(
+            to_arg(tag), static_cast<const uint8_t*>(in), n, in_len, static_cast<uint8_t*>(out), out_len);
+        return cudaGetLastError();
+    }
     if (truncate)
         k_sponge_digest<true><<<grid_for(n), kThreads, 0, st>>>(to_arg(tag), static_cast<const uint8_t*>(in), n, in_len,
                                                                 static_cast<uint8_t*>(out), out_len);

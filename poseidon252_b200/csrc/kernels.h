@@ -9,8 +9,9 @@
 namespace p252 {
 
 cudaError_t launch_permute(void* states, size_t n, bool dense, cudaStream_t st);
+// coop_max: batches of at most this many items run the lane-split (5 threads per state) kernel
 cudaError_t launch_digest(const uint64_t tag[4], const void* in, size_t n, uint32_t in_len, void* out,
-                          uint32_t out_len, bool truncate, cudaStream_t st);
+                          uint32_t out_len, bool truncate, size_t coop_max, cudaStream_t st);
 cudaError_t launch_convert(const void* in, size_t n, void* out, uint8_t* ok, bool from_bytes, cudaStream_t st);
 cudaError_t launch_encrypt(const uint64_t tag[4], const void* msg, size_t n, uint32_t L, const void* secret_uv,
                            const void* nonce, void* cipher, cudaStream_t st);
@@ -24,6 +25,7 @@ cudaError_t launch_merkle_verify(const uint64_t tag[4], const uint64_t root[4], 
                                  const uint64_t* leaf_idx, const void* paths, size_t n, int arity, uint32_t depth,
                                  uint8_t* ok, unsigned long long* n_failed, cudaStream_t st);
 void kernel_launch_shape(int* threads_per_block, int* min_blocks_per_sm);
+size_t coop_max_items();   // default small-batch threshold (P252_COOP_MAX or the built-in value)
 // 32x32->64-bit multiply instructions (IMAD.WIDE / IMAD.HI class) and DFMA per Hades permutation, counted from
 // the generated PTX (fr_ptx.cuh) and the round structure of hades_permute()
 uint32_t wide_mul_per_permutation();

@@ -368,6 +368,10 @@ class Engine:
     def last_verify_failures(self):
         return int(getattr(self, "_vfail", ctypes.c_size_t(0)).value)
 
+    def set_small_batch_max(self, max_items):
+        """Digest batches up to `max_items` items use the lane-split (5 threads per state) kernel; 0 disables it."""
+        self._check(self._lib.p252_set_small_batch_max(self._ctx, int(max_items)))
+
     # -- introspection ----------------------------------------------------------------------------
     def kernel_info(self):
         """p252_get_kernel_info as a dict (multiplier / DFMA instructions per permutation, launch shape)."""
