@@ -114,7 +114,8 @@ int p252_get_kernel_info(p252_kernel_info* out);
 
 /* Digest batches of at most `max_items` items run the lane-split kernel (five threads per sponge state: lower latency,
  * ~3x lower throughput per state) -- the regime of single digests and of the top levels of a Merkle tree.  Default
- * 4096 (environment variable P252_COOP_MAX overrides it at context creation); 0 disables the lane-split path.  Both
+ * 3552 = one lane-split warp per SM sub-partition, the measured crossover (environment variable P252_COOP_MAX
+ * overrides it at context creation); 0 disables the lane-split path.  Both
  * kernels produce bit-identical results. */
 int p252_set_small_batch_max(p252_ctx* ctx, size_t max_items);
 

@@ -455,7 +455,7 @@ static inline unsigned grid_for(size_t n) { return (unsigned)((n + kThreads - 1)
 // regime); the environment variable P252_COOP_MAX overrides it (0 disables the lane-split path).  Measured crossover:
 // profiles/README.md "small batches".
 #ifndef P252_COOP_MAX_DEFAULT
-#define P252_COOP_MAX_DEFAULT 4096
+#define P252_COOP_MAX_DEFAULT 3552   // 148 SMs x 4 sub-partitions x 6 items per warp: one lane-split warp per sub-partition
 #endif
 size_t coop_max_items() {
     static const size_t v = [] {

@@ -37,7 +37,7 @@ def coracle():
 @pytest.fixture(scope="session", params=["default", "throughput-kernel-only"])
 def engine(request):
     """The CUDA engine.  No skip-on-failure: a GPU test without the native library or without a
-    B200 must fail loudly.  Every test runs twice: with the default dispatch (digest batches <= 4096 items take the
+    B200 must fail loudly.  Every test runs twice: with the default dispatch (digest batches <= 3552 items take the
     lane-split small-batch kernel) and with that kernel disabled, so that both digest kernels see every shape."""
     import poseidon252_b200 as pb
     eng = pb.Engine(0)
