@@ -58,6 +58,25 @@ def main():
         "encrypt2": hx(o.hash_to_scalar(o.tag_input(
             [o.Absorb(2), o.Absorb(1), o.Squeeze(2), o.Absorb(2), o.Squeeze(1)], o.Domain.Encryption))),
     }
+    # Merkle trees (node = Hash::digest(Domain::Merkle4 | Merkle2, children), src/hash.rs:22-31): all internal levels
+    # bottom-up + one opening (per level: the sibling group of the path node) -- for the tree / opening entry points
+    trees = []
+    for arity, k, leaf in ((4, 3, 37), (2, 5, 19)):
+        dom = o.Domain.Merkle4 if arity == 4 else o.Domain.Merkle2
+        leaves = [rnd.randrange(o.P) for _ in range(arity ** k)]
+        leaves[5] = 0                                            # an empty slot is the zero scalar
+        levels, cur = [leaves], leaves
+        while len(cur) > 1:
+            cur = [o.Hash.digest(dom, cur[i:i + arity])[0] for i in range(0, len(cur), arity)]
+            levels.append(cur)
+        path, i = [], leaf
+        for l in range(k):
+            g0 = i // arity * arity
+            path.append([hx(v) for v in levels[l][g0:g0 + arity]])
+            i //= arity
+        trees.append({"arity": arity, "leaves": [hx(v) for v in leaves],
+                      "nodes": [hx(v) for lv in levels[1:] for v in lv], "opening_leaf": leaf, "opening": path})
+    g["merkle"] = trees
     with open(os.path.join(HERE, "hades_golden.json"), "w") as f:
         json.dump(g, f, indent=1)
     print("wrote hades_golden.json")

@@ -140,3 +140,17 @@ def test_opening_mirror_and_errors(engine):
     with pytest.raises(pb.EngineError):                          # node array of the wrong size
         engine.merkle_open_batch(leaves, nodes[:-1], np.array([1], dtype=np.uint64))
     assert engine.merkle_open_batch(leaves, nodes, np.zeros(0, dtype=np.uint64)).shape == (0, 3, 4, 4)
+
+
+def test_merkle_golden(engine, golden):
+    """tests/golden: trees + one opening each (oracle-derived, tests/golden/make_golden.py)"""
+    from conftest import hx, unmont
+    for t in golden["merkle"]:
+        arity = t["arity"]
+        leaves = mont([hx(v) for v in t["leaves"]])
+        nodes = engine.merkle_build(leaves, arity=arity)
+        assert ["0x%064x" % v for v in unmont(nodes)] == t["nodes"]
+        i = t["opening_leaf"]
+        paths = engine.merkle_open_batch(leaves, nodes, np.array([i], dtype=np.uint64), arity=arity)
+        assert [["0x%064x" % v for v in unmont(row)] for row in paths[0]] == t["opening"]
+        assert engine.merkle_verify_batch(leaves[i:i + 1], np.array([i], dtype=np.uint64), paths, nodes[-1], arity=arity)[0]

@@ -151,3 +151,18 @@ def test_c_oracle_matches_python(oracle, coracle, golden):
     # multi-thread wrapper == single thread
     s = mont([[int(v) for v in rng.integers(0, 1 << 62, 5)] for _ in range(64)])
     assert np.array_equal(coracle.permute(s), coracle.permute(s, threads=4))
+
+
+def test_merkle_golden_vs_c_oracle(golden, coracle, oracle):
+    """CPU: the committed tree / opening vectors (Python oracle) agree with the C port level by level."""
+    from conftest import hx, mont, unmont
+    for t in golden["merkle"]:
+        arity = t["arity"]
+        dom = oracle.Domain.Merkle4 if arity == 4 else oracle.Domain.Merkle2
+        tag = mont(oracle.hash_to_scalar(oracle.tag_input([oracle.Absorb(arity), oracle.Squeeze(1)], dom)))
+        cur, nodes = mont([hx(v) for v in t["leaves"]]), []
+        while cur.shape[0] > 1:
+            cur = coracle.digest(tag, cur.reshape(-1, arity, 4), arity, 1).reshape(-1, 4)
+            nodes += ["0x%064x" % v for v in unmont(cur)]
+        assert nodes == t["nodes"]
+        assert t["opening"][0][t["opening_leaf"] % arity] == t["leaves"][t["opening_leaf"]]
