@@ -293,7 +293,7 @@ __device__ __forceinline__ void hades_permute_coop(uint32_t (&s)[8], int li, int
             for (int k = 0; k < 8; ++k) s[k] = w[k];
         } else {
             uint32_t c[8], z[8];
-            load_const(c, P252_G_ROW(r - kHalfFull));
+            load_const(c, kG[r - kHalfFull]);         // always the constant bank (warp-uniform index)
             montmul(z, c, w);
 #pragma unroll
             for (int k = 0; k < 8; ++k) s[k] = (li == 4) ? z[k] : s[k];
