@@ -170,9 +170,11 @@ int run_host_pipeline(p252_ctx* ctx, std::vector<Io>& ios, size_t n, Launch laun
         // fork: slots wait for everything already enqueued on the context stream
         CU(cudaEventRecord(ctx->ev_fork, ctx->stream));
         for (int s = 0; s < kSlots; ++s) CU(cudaStreamWaitEvent(ctx->slots[s].stream, ctx->ev_fork, 0));
-        size_t k = 0;
-        for (size_t off = 0; off < n; off += chunk, ++k) {
-            const size_t cnt = std::min(chunk, n - off);
+        // Ramp-up: the first chunks are small (chunk/8, /4, /2) so that the first kernel starts after a ~1 MiB
+        // copy instead of a full chunk's; from the fourth chunk on every chunk has the full size.
+        size_t k = 0, cur = std::max<size_t>(1024, chunk / 8 / 128 * 128);
+        for (size_t off = 0, cnt = 0; off < n; off += cnt, ++k, cur = std::min(chunk, cur * 2)) {
+            cnt = std::min(cur, n - off);
             Slot& sl = ctx->slots[k % kSlots];
             // arena layout: one 256-byte aligned region per buffer
             size_t need = 0;

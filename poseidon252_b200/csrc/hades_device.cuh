@@ -167,7 +167,10 @@ __device__ __forceinline__ void mix(uint32_t (&s)[5][8], int next_round P252_TAB
 }
 
 // In-register Hades permutation, standard Montgomery form in and out (both < p).
-__device__ __forceinline__ void hades_permute(uint32_t (&s)[5][8] P252_TAB_ARG) {
+// out_lanes: bit i set = lane i of the result is needed.  The last permutation of a sponge is only ever read through
+// the rate lanes it squeezes (a Merkle digest: lane 1), so the output multiplication + final subtraction of the other
+// lanes is skipped (warp-uniform branch); lanes not asked for are left in the internal scaled form and must not be used.
+__device__ __forceinline__ void hades_permute(uint32_t (&s)[5][8], uint32_t out_lanes P252_TAB_ARG) {
     uint32_t c[8];
     // first add_round_constants: explicit, then one full conditional subtraction
 #pragma unroll
@@ -210,8 +213,13 @@ __device__ __forceinline__ void hades_permute(uint32_t (&s)[5][8] P252_TAB_ARG) 
 #pragma unroll 1
     for (int it = 0; it < 5; ++it) {
         uint32_t w[8];
-        montmul(w, c, s[4]);
-        fr_condsub(w);
+        if ((out_lanes >> (4 - it)) & 1u) {            // slot 4 holds lane 4 - it
+            montmul(w, c, s[4]);
+            fr_condsub(w);
+        } else {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) w[k] = s[4][k];
+        }
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
             s[4][k] = s[3][k];

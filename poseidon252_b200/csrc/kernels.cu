@@ -134,7 +134,15 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) k_sponge_digest(FrArg ta
     uint8_t* out_w = out + item0 * (size_t)out_len * 32;
 #pragma unroll 1
     for (uint32_t step = 0; step < nin + nout; ++step) {
-        if (step > 0) hades_permute(s P252_TAB_PASS);
+        if (step > 0) {
+            // the last permutation is read only through the rate lanes of the final squeeze chunk
+            uint32_t need = 0x1fu;
+            if (step + 1 == nin + nout) {
+                const uint32_t left = out_len - 4 * (nout - 1);
+                need = ((1u << (left < 4 ? left : 4)) - 1u) << 1;
+            }
+            hades_permute(s, need P252_TAB_PASS);
+        }
         if (step < nin) {
             const uint32_t left = in_len - 4 * step;
             const int nscal = left < 4 ? (int)left : 4;
@@ -239,7 +247,7 @@ __global__ void __launch_bounds__(kThreads, kDense ? 1 : kMinBlocks) k_permute(u
     if (kDense)
         dense_permute(s);
     else
-        hades_permute(s P252_TAB_PASS);
+        hades_permute(s, 0x1fu P252_TAB_PASS);
     {
         uint32_t v[4][8];
 #pragma unroll
@@ -279,7 +287,7 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) k_crypt(FrArg tag, const
     bool good = true;
 #pragma unroll 1
     for (uint32_t step = 0; step < 2 * nk; ++step) {
-        hades_permute(s P252_TAB_PASS);
+        hades_permute(s, (step + 1 == 2 * nk) ? 0x2u : 0x1fu P252_TAB_PASS);   // last: only the Squeeze(1) lane is read
         if (step < nk) {
             // Squeeze chunk `step` of the keystream and emit cipher (or recovered message)
             const uint32_t left = L - 4 * step;
@@ -424,7 +432,7 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) k_merkle_verify(FrArg ta
 #pragma unroll
             for (int q = 0; q < 4; ++q) s[1 + q][k] = (q < kArity) ? v[q][k] : 0u;
         }
-        hades_permute(s P252_TAB_PASS);
+        hades_permute(s, 0x2u P252_TAB_PASS);          // a Merkle digest reads lane 1 only
 #pragma unroll
         for (int k = 0; k < 8; ++k) cur[k] = s[1][k];
     }

@@ -37,7 +37,7 @@ __global__ void __launch_bounds__(128, 5) prim(uint32_t* io, int iters) {
 #pragma unroll 1
         for (int it = 0; it < iters; ++it) {
             if (MODE == 3) mix(s, 1 + (it & 63));
-            if (MODE == 4) hades_permute(s);
+            if (MODE == 4) hades_permute(s, 0x1fu);
         }
 #pragma unroll
         for (int i = 0; i < 5; ++i)
