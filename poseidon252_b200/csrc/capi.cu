@@ -170,9 +170,10 @@ int run_host_pipeline(p252_ctx* ctx, std::vector<Io>& ios, size_t n, Launch laun
         // fork: slots wait for everything already enqueued on the context stream
         CU(cudaEventRecord(ctx->ev_fork, ctx->stream));
         for (int s = 0; s < kSlots; ++s) CU(cudaStreamWaitEvent(ctx->slots[s].stream, ctx->ev_fork, 0));
-        // Ramp-up: the first chunks are small (chunk/8, /4, /2) so that the first kernel starts after a ~1 MiB
-        // copy instead of a full chunk's; from the fourth chunk on every chunk has the full size.
-        size_t k = 0, cur = std::max<size_t>(1024, chunk / 8 / 128 * 128);
+        // Ramp-up (batches of several chunks only): the first chunks are small (chunk/8, /4, /2) so that the first
+        // kernel starts after a ~1 MiB copy instead of a full chunk's; from the fourth chunk on every chunk has the
+        // full size.  A batch that fits one chunk is one launch.
+        size_t k = 0, cur = (n > 2 * chunk) ? std::max<size_t>(1024, chunk / 8 / 128 * 128) : chunk;
         for (size_t off = 0, cnt = 0; off < n; off += cnt, ++k, cur = std::min(chunk, cur * 2)) {
             cnt = std::min(cur, n - off);
             Slot& sl = ctx->slots[k % kSlots];
