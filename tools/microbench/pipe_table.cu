@@ -128,6 +128,36 @@ __global__ void __launch_bounds__(128) kern(uint32_t* out, uint32_t b, int iters
                 if (MODE == 17)  // DADD
                     asm volatile("add.f64 %0, %0, %1;" : "+d"(d[k]) : "d"(dc));
             }
+
+            // ---- review item (iii): what a DFMA-based (FP64-limb) squaring PRODUCT would issue vs the IMAD one ----
+            // Synthetic instruction mixes with the counts of DESIGN.md 4.1 (independent accumulators: an optimistic
+            // throughput bound for both).  30: 36 IMAD.WIDE + 40 ALU (the shipped 8x32-bit squaring product).
+            // 31: 72 DFMA + 24 DADD + 116 ALU (16-bit split of one operand, conversions by magic-number DADD, column
+            // recombination).  32: blocks alternate 30 / 31, i.e. both pipes loaded on every sub-partition.
+            if (MODE == 30 || (MODE == 32 && (blockIdx.x & 1) == 0)) {
+                if (r % 2 == 0) {
+#pragma unroll
+                    for (int z = 0; z < 36; ++z) WIDE_RR(z & 7);
+#pragma unroll
+                    for (int q = 0; q < 20; ++q) {
+                        asm volatile("{.reg .u32 t; add.u32 t, %0, %1; add.u32 %0, t, %2;}" : "+r"(s[q & 7]) : "r"(s[(q + 3) & 7]), "r"(x[q & 7]));
+                        asm volatile("shf.l.wrap.b32 %0, %0, %1, 1;" : "+r"(s[(q + 1) & 7]) : "r"(s[(q + 5) & 7]));
+                    }
+                }
+            }
+            if (MODE == 31 || (MODE == 32 && (blockIdx.x & 1) == 1)) {
+                if (r % 2 == 0) {
+#pragma unroll
+                    for (int q = 0; q < 72; ++q) asm volatile("fma.rn.f64 %0, %0, %1, %2;" : "+d"(d[q & 7]) : "d"(dc), "d"(de));
+#pragma unroll
+                    for (int q = 0; q < 24; ++q) asm volatile("add.f64 %0, %0, %1;" : "+d"(d[q & 7]) : "d"(dc));
+#pragma unroll
+                    for (int q = 0; q < 58; ++q) {
+                        asm volatile("{.reg .u32 t; add.u32 t, %0, %1; add.u32 %0, t, %2;}" : "+r"(s[q & 7]) : "r"(s[(q + 3) & 7]), "r"(x[q & 7]));
+                        asm volatile("shf.l.wrap.b32 %0, %0, %1, 1;" : "+r"(s[(q + 1) & 7]) : "r"(s[(q + 5) & 7]));
+                    }
+                }
+            }
             if (MODE == 18) {  // carry chain: 4 IMAD.WIDE.X per chain, two chains
                 asm volatile("mad.lo.cc.u32 %0, %8, %12, %0; madc.hi.cc.u32 %1, %8, %12, %1; madc.lo.cc.u32 %2, %9, %12, %2; madc.hi.cc.u32 %3, %9, %12, %3;"
                              "madc.lo.cc.u32 %4, %10, %12, %4; madc.hi.cc.u32 %5, %10, %12, %5; madc.lo.cc.u32 %6, %11, %12, %6; madc.hi.u32 %7, %11, %12, %7;"
@@ -200,6 +230,10 @@ int main() {
     run<25>("WIDE + 2 x 1-reg ALU", 24, d_out);
     run<26>("IMAD lo + IADD3 + DFMA", 24, d_out);
     run<27>("mul.wide(2 reads) + IADD3", 16, d_out);
+    // per "squaring product": REP/2 = 8 products per loop iteration -> pass 1/8 of a group as the unit
+    run<30>("IMAD sqr product (36W+40ALU) x8", 8, d_out);
+    run<31>("FP64 sqr product (72DFMA+24DADD+116ALU) x8", 8, d_out);
+    run<32>("both, alternating blocks x8", 8, d_out);
     printf("status: %s\n", cudaGetErrorString(cudaDeviceSynchronize()));
     return 0;
 }
