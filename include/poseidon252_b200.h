@@ -200,7 +200,9 @@ int p252_merkle_build(p252_ctx* ctx, int arity, const p252_fr* leaves, size_t n_
  * holds, for every level l = 0..depth-1 (0 = the leaf level), the WHOLE sibling group of the path node: the
  * `arity` items at [g*arity, (g+1)*arity) of level l with g = i / arity^(l+1); the path node sits at offset
  * (i / arity^l) % arity inside its group.  Empty slots of a sparse tree are the zero scalar (src/hash.rs:22-31).
- * paths: n x depth x arity scalars, item-major.  leaf_idx lives in the same memory space as the other buffers. */
+ * paths: n x depth x arity scalars, item-major.  leaf_idx lives in the same memory space as the other buffers.  An index
+ * >= n_leaves is P252_ERR_INVALID_ARGUMENT for HOST buffers; for DEVICE buffers (not inspected on the host) its opening
+ * is all zero, which no root verifies. */
 int p252_merkle_open_batch(p252_ctx* ctx, int arity, const p252_fr* leaves, size_t n_leaves, const p252_fr* nodes,
                            const uint64_t* leaf_idx, size_t n, p252_fr* paths_out, int flags);
 /* n x Opening::verify: cur = leaf_items[i]; for every level: paths[i][l][pos] must equal cur, then

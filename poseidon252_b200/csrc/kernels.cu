@@ -365,8 +365,13 @@ __global__ void __launch_bounds__(256) k_merkle_open(const uint8_t* __restrict__
     const size_t item = t / depth;
     const uint32_t level = (uint32_t)(t % depth);
     const uint32_t arity = 1u << log2_arity;
-    uint64_t idx = leaf_idx[item];
-    if (idx >= n_leaves) idx = 0;                         // rejected on the host for HOST buffers; clamp for device ones
+    const uint64_t idx = leaf_idx[item];
+    uint8_t* dst = paths + ((size_t)item * depth + level) * arity * 32;
+    if (idx >= n_leaves) {                                // HOST buffers are rejected on the host; a device index outside
+        for (uint32_t q = 0; q < arity * 2; ++q)          // the tree gets an all-zero opening (it cannot verify)
+            reinterpret_cast<uint4*>(dst)[q] = make_uint4(0, 0, 0, 0);
+        return;
+    }
     const uint64_t group = idx >> (log2_arity * (level + 1));
     const uint8_t* src;
     if (level == 0) {
@@ -377,7 +382,6 @@ __global__ void __launch_bounds__(256) k_merkle_open(const uint8_t* __restrict__
         for (uint32_t q = 0; q + 1 < level; ++q, m >>= log2_arity) off += m;
         src = nodes + (off + group * arity) * 32;
     }
-    uint8_t* dst = paths + ((size_t)item * depth + level) * arity * 32;
     for (uint32_t q = 0; q < arity * 2; ++q)
         reinterpret_cast<uint4*>(dst)[q] = ldg128(src + q * 16);
 }

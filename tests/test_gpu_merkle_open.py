@@ -118,6 +118,12 @@ def test_open_verify_device_tensors(engine, arity, k):
     d_items = d_leaves[d_idx]
     ok = engine.merkle_verify_batch(d_items, d_idx, d_paths, nodes[-1], arity=arity)
     assert ok.is_cuda and bool(ok.all()) and engine.last_verify_failures() == 0
+    # a device index outside the tree: all-zero opening, verification fails
+    far = d_idx.clone()
+    far[0] = n_leaves + 5
+    z = engine.merkle_open_batch(d_leaves, d_nodes, far, arity=arity)
+    assert not bool(z[0].any()) and torch.equal(z[1:], d_paths[1:])
+    assert not bool(engine.merkle_verify_batch(d_items, far, z, nodes[-1], arity=arity)[0])
     d_paths[3, 1, 0, 0] ^= 1
     d_paths[999, 0, arity - 1, 2] ^= 4
     ok = engine.merkle_verify_batch(d_items, d_idx, d_paths, nodes[-1], arity=arity).cpu().numpy()
