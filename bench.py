@@ -407,10 +407,29 @@ def main():
     torch.cuda.set_device(local)
     stream = torch.cuda.Stream()
     eng = pb.Engine(local, stream=stream.cuda_stream)
+    tree_skip = None
     if dist is not None and args.workload in ("merkle4", "tree") and not (args.workload == "merkle4" and args.no_tree):
-        box = [eng.dist_unique_id() if rank == 0 else bytes(128)]
+        # the library's own NCCL communicator (bound with dlopen to the NCCL copy torch already loaded); if any rank
+        # cannot set it up, every rank skips the tree block instead of losing the headline
+        ok = 1.0
+        try:
+            box = [eng.dist_unique_id() if rank == 0 else bytes(128)]
+        except Exception as exc:
+            box, ok, tree_skip = [bytes(128)], 0.0, repr(exc)
         dist.broadcast_object_list(box, src=0)
-        eng.dist_init(box[0], rank, world)
+        flag = torch.tensor([ok], dtype=torch.float64, device="cuda")
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if flag.item() == 1.0:
+            try:
+                eng.dist_init(box[0], rank, world)
+            except Exception as exc:
+                ok, tree_skip = 0.0, repr(exc)
+            flag = torch.tensor([ok], dtype=torch.float64, device="cuda")
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if flag.item() != 1.0:
+            tree_skip = tree_skip or "another rank could not initialise the tree communicator"
+            if args.workload == "tree":
+                raise RuntimeError(tree_skip)
     n = 1 << args.log2_batch
     rng = np.random.default_rng(0xC10D + rank)          # benches/hash.rs:53 seed, per-rank stream
 
@@ -577,7 +596,9 @@ def main():
 
     # ---- tree block (all ranks take part; outside the headline's timed region) ----------------------------------
     tree = None
-    if args.workload == "merkle4" and not args.no_tree:
+    if args.workload == "merkle4" and not args.no_tree and tree_skip is not None:
+        tree = {"error": "tree block skipped: " + tree_skip}
+    elif args.workload == "merkle4" and not args.no_tree:
         try:
             del ins
             torch.cuda.empty_cache()

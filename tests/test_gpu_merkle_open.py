@@ -160,3 +160,20 @@ def test_merkle_golden(engine, golden):
         paths = engine.merkle_open_batch(leaves, nodes, np.array([i], dtype=np.uint64), arity=arity)
         assert [["0x%064x" % v for v in unmont(row)] for row in paths[0]] == t["opening"]
         assert engine.merkle_verify_batch(leaves[i:i + 1], np.array([i], dtype=np.uint64), paths, nodes[-1], arity=arity)[0]
+
+
+def test_verify_host_multi_chunk(engine):
+    """80k host openings: several staged chunks (ramp-up sizes, then full chunks) through run_host_pipeline."""
+    rng = np.random.default_rng(31)
+    leaves = random_scalars(rng, 4 ** 5)
+    nodes = engine.merkle_build(leaves, arity=4)
+    idx = rng.integers(0, 4 ** 5, size=80_000, dtype=np.uint64)
+    paths = engine.merkle_open_batch(leaves, nodes, idx)
+    items = leaves[idx.astype(np.int64)]
+    bad = rng.choice(80_000, size=300, replace=False)
+    items = items.copy()
+    items[bad, 0] ^= np.uint64(1)
+    ok = engine.merkle_verify_batch(items, idx, paths, nodes[-1])
+    expect = np.ones(80_000, dtype=np.uint8)
+    expect[bad] = 0
+    assert np.array_equal(ok, expect) and engine.last_verify_failures() == 300
