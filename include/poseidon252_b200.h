@@ -112,7 +112,7 @@ typedef struct p252_kernel_info {
 } p252_kernel_info;
 int p252_get_kernel_info(p252_kernel_info* out);
 
-/* Digest batches of at most `max_items` items run the lane-split kernel (five threads per sponge state: lower latency,
+/* Digest and raw-permutation batches of at most `max_items` items run the lane-split kernels (five threads per sponge state: lower latency,
  * ~3x lower throughput per state) -- the regime of single digests and of the top levels of a Merkle tree.  Default
  * 3552 = one lane-split warp per SM sub-partition, the measured crossover (environment variable P252_COOP_MAX
  * overrides it at context creation); 0 disables the lane-split path.  Both

@@ -547,11 +547,11 @@ static int permute_impl(p252_ctx* ctx, p252_fr* states, size_t n, int flags, boo
     if (flags & P252_MEM_DEVICE) {
         if (!aligned16(states)) return P252_ERR_INVALID_ARGUMENT;
         if (n == 0) return P252_OK;
-        return finish_device_call(ctx, p252::launch_permute(states, n, dense, ctx->stream), flags);
+        return finish_device_call(ctx, p252::launch_permute(states, n, dense, ctx->coop_max, ctx->stream), flags);
     }
     std::vector<Io> ios = {{states, states, 160}};
     return run_host_pipeline(ctx, ios, n, [&](void** d, size_t cnt, cudaStream_t st) {
-        return p252::launch_permute(d[0], cnt, dense, st);
+        return p252::launch_permute(d[0], cnt, dense, ctx->coop_max, st);
     });
 }
 

@@ -219,6 +219,24 @@ __global__ void __launch_bounds__(kThreads) k_sponge_digest_coop(FrArg tag, cons
     }
 }
 
+// raw permutation, small batches: thread li of a group loads / stores lane li of its state (32 B)
+__global__ void __launch_bounds__(kThreads) k_permute_coop(uint8_t* __restrict__ states, size_t n) {
+    const int lane = threadIdx.x & 31;
+    const int grp = lane / 5, li = lane - grp * 5, g0 = grp * 5;
+    const size_t warp_global = (size_t)blockIdx.x * kWarps + (threadIdx.x >> 5);
+    const size_t item = warp_global * kCoopItemsPerWarp + grp;
+    if (warp_global * kCoopItemsPerWarp >= n) return;
+    const bool live = (grp < kCoopItemsPerWarp) && (item < n);
+    double crow[5];
+#pragma unroll
+    for (int j = 0; j < 5; ++j) crow[j] = (double)(HADES_LAMBDA / (uint32_t)(li + j + 5));
+    uint8_t* p = states + (live ? item : 0) * 160 + (size_t)li * 32;
+    uint32_t s[8];
+    load_fr_rw(s, p);
+    hades_permute_coop(s, li, g0, crow);
+    if (live) store_fr(p, s);
+}
+
 // ---- raw permutation of n x 5 states in place (Safe::permute) -----------------------------------
 template <bool kDense>
 __global__ void __launch_bounds__(kThreads, kDense ? 1 : kMinBlocks) k_permute(uint8_t* __restrict__ states, size_t n) {
@@ -477,8 +495,13 @@ size_t coop_max_items() {
     return v;
 }
 
-cudaError_t launch_permute(void* states, size_t n, bool dense, cudaStream_t st) {
+cudaError_t launch_permute(void* states, size_t n, bool dense, size_t coop_max, cudaStream_t st) {
     if (n == 0) return cudaSuccess;
+    if (!dense && n <= coop_max) {
+        const size_t warps = (n + kCoopItemsPerWarp - 1) / kCoopItemsPerWarp;
+        k_permute_coop<<<(unsigned)((warps + kWarps - 1) / kWarps), kThreads, 0, st>>>(static_cast<uint8_t*>(states), n);
+        return cudaGetLastError();
+    }
     if (dense)
         k_permute<true><<<grid_for(n), kThreads, 0, st>>>(static_cast<uint8_t*>(states), n);
     else

@@ -8,7 +8,7 @@
 
 namespace p252 {
 
-cudaError_t launch_permute(void* states, size_t n, bool dense, cudaStream_t st);
+cudaError_t launch_permute(void* states, size_t n, bool dense, size_t coop_max, cudaStream_t st);
 // coop_max: batches of at most this many items run the lane-split (5 threads per state) kernel
 cudaError_t launch_digest(const uint64_t tag[4], const void* in, size_t n, uint32_t in_len, void* out,
                           uint32_t out_len, bool truncate, size_t coop_max, cudaStream_t st);
