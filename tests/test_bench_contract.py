@@ -34,3 +34,26 @@ def test_non_zero_ranks_of_the_reference_arm_exit_quietly():
     res = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
                           "--gpus", "2", "--log2-batch", "10"], capture_output=True, text=True, timeout=120, cwd=ROOT, env=env)
     assert res.returncode == 0 and res.stdout.strip() == ""
+
+
+import pytest
+
+
+@pytest.mark.gpu
+def test_gpu_arm_line_small():
+    """the GPU arm end to end on a reduced batch: one JSON line, contract keys, roofline / imad / e2e / tree blocks,
+    tree parity ok"""
+    res = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "3", "--warmup", "3", "--log2-batch", "14",
+                          "--log4-leaves", "7", "--no-cpu-baseline"], capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert res.returncode == 0, res.stderr[-3000:]
+    lines = [ln for ln in res.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline",
+              "dtype", "data", "config", "clocks", "gpu_launches", "roofline", "e2e", "tree"):
+        assert k in d, k
+    assert d["gpu_launches"] == 3 and d["n_gpus"] == 1 and d["value"] > 1e6
+    assert d["roofline"]["bound"] == "hbm" and 0 < d["roofline"]["frac"] < 1
+    assert d["roofline"]["imad"]["bound"] == "imad" and 0 < d["roofline"]["imad"]["frac"] < 1
+    assert d["e2e"]["h2d_bytes_per_step"] == (1 << 14) * 128 and d["e2e"]["d2h_bytes_per_step"] == (1 << 14) * 32
+    assert d["tree"]["parity"] == "ok" and d["tree"]["leaves_log4"] == 7 and len(d["tree"]["per_level_rank0"]) == 7
