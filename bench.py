@@ -366,7 +366,7 @@ def tree_block(eng, torch, dist, rank, world, stream, k, builds=3, paths=64):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=40)
+    ap.add_argument("--steps", type=int, default=None, help="timed steps (default 40; 2 for --workload sweep: one step = 2.2e9 permutations)")
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="merkle4", choices=["merkle4", "encrypt", "decrypt", "permute", "sweep", "tree", "convert"])
@@ -376,6 +376,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-tree", action="store_true", help="merkle4: skip the tree block")
     args = ap.parse_args()
+    if args.steps is None:
+        args.steps = 2 if args.workload == "sweep" else 40
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     rank, world, local = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
 
