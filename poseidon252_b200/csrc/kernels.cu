@@ -242,13 +242,14 @@ __global__ void __launch_bounds__(kThreads) k_permute_coop(uint8_t* __restrict__
 }
 
 // ---- raw permutation of n x 5 states in place (Safe::permute) -----------------------------------
-template <bool kDense>
-__global__ void __launch_bounds__(kThreads, kDense ? 1 : kMinBlocks) k_permute(uint8_t* __restrict__ states, size_t n) {
-    __shared__ uint4 stage[kWarps][32][8];
+template <bool kDense, int kT = kThreads, int kMB = kMinBlocks>
+__global__ void __launch_bounds__(kT, kDense ? 1 : kMB) k_permute(uint8_t* __restrict__ states, size_t n) {
+    constexpr int kW = kT / 32;
+    __shared__ uint4 stage[kW][32][8];
     P252_STAGE_TABLES
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
-    const size_t item0 = ((size_t)blockIdx.x * kWarps + warp) * 32;
+    const size_t item0 = ((size_t)blockIdx.x * kW + warp) * 32;
     if (item0 >= n) return;
     const int nitems = (n - item0 < 32) ? (int)(n - item0) : 32;
     uint4(*st)[8] = stage[warp];
@@ -513,6 +514,8 @@ cudaError_t launch_permute(void* states, size_t n, bool dense, size_t coop_max, 
     }
     if (dense)
         k_permute<true><<<grid_for(n), kThreads, 0, st>>>(static_cast<uint8_t*>(states), n);
+    else if (n >= kWideShapeMinItems)
+        k_permute<false, 256, 2><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(static_cast<uint8_t*>(states), n);
     else
         k_permute<false><<<grid_for(n), kThreads, 0, st>>>(static_cast<uint8_t*>(states), n);
     return cudaGetLastError();
