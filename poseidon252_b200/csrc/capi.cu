@@ -13,6 +13,7 @@
 
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <string>
@@ -25,7 +26,15 @@
 namespace {
 
 constexpr int kSlots = 3;                    // H2D / compute / D2H overlap for HOST buffers
-constexpr size_t kChunkItemsMax = 1 << 16;   // items per staged chunk (upper bound)
+constexpr size_t kChunkItemsDefault = 1 << 17;   // items per staged chunk (upper bound, also capped by kChunkBytesTarget); P252_CHUNK_ITEMS overrides (measured: 2^15 6.67, 2^16 6.45, 2^17 6.40, bytes-capped 157k 6.48 ms per 2^20-digest e2e step)
+size_t chunk_items_max() {
+    static const size_t v = [] {
+        const char* e = getenv("P252_CHUNK_ITEMS");
+        const size_t x = e ? (size_t)strtoull(e, nullptr, 10) : kChunkItemsDefault;
+        return x >= 1024 ? x : kChunkItemsDefault;
+    }();
+    return v;
+}
 constexpr size_t kChunkBytesTarget = 24u << 20;
 
 struct Slot {
@@ -160,7 +169,7 @@ int run_host_pipeline(p252_ctx* ctx, std::vector<Io>& ios, size_t n, Launch laun
     if (n == 0) return P252_OK;
     size_t per_item = 0;
     for (auto& io : ios) per_item += (io.item_bytes + 15) / 16 * 16;
-    size_t chunk = std::max<size_t>(1024, std::min(kChunkItemsMax, kChunkBytesTarget / std::max<size_t>(per_item, 1)));
+    size_t chunk = std::max<size_t>(1024, std::min(chunk_items_max(), kChunkBytesTarget / std::max<size_t>(per_item, 1)));
     chunk = (chunk + 127) / 128 * 128;
     if (chunk > n) chunk = n;
     const long long fail_at = ctx->fail_chunk;
