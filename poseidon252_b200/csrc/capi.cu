@@ -26,7 +26,9 @@
 namespace {
 
 constexpr int kSlots = 3;                    // H2D / compute / D2H overlap for HOST buffers
-constexpr size_t kChunkItemsDefault = 1 << 17;   // items per staged chunk (upper bound, also capped by kChunkBytesTarget); P252_CHUNK_ITEMS overrides (measured: 2^15 6.67, 2^16 6.45, 2^17 6.40, bytes-capped 157k 6.48 ms per 2^20-digest e2e step)
+constexpr size_t kChunkItemsDefault = 1 << 17;   // items per staged chunk (upper bound, also capped by kChunkBytesTarget);
+                                                // P252_CHUNK_ITEMS overrides.  e2e ms per 2^20-digest step: 2^15 6.67, 2^16 6.43,
+                                                // 2^17 6.43 (equal within run-to-run noise), 157k (bytes cap) 6.48
 size_t chunk_items_max() {
     static const size_t v = [] {
         const char* e = getenv("P252_CHUNK_ITEMS");
